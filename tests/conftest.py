@@ -1,0 +1,49 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def golden_model(name):
+    """-> (cfg dict, state_dict of torch tensors, raw npz)"""
+    z = load_golden(f"model_{name}.npz")
+    cfg = {}
+    for k in z.files:
+        if k.startswith("cfg_"):
+            v = z[k]
+            cfg[k[4:]] = v.item() if v.dtype.kind in "iub" else str(v)
+    cfg["causal"] = bool(cfg["causal"])
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    return cfg, sd, z
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  — the 'max-rel-err' every tolerance in this suite is stated in."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
