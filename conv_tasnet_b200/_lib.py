@@ -1,0 +1,105 @@
+"""ctypes binding of libctn_b200.so (include/ctn_b200.h).  No CPU fallback: if the library is missing or a
+tensor is not on a CUDA device the call raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libctn_b200.so")
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class CtnConfig(ctypes.Structure):
+    _fields_ = [(k, c_i32) for k in ("N", "L", "B", "H", "P", "X", "R", "C", "norm_type", "causal", "mask_nonlinear")]
+
+
+_P = ctypes.POINTER(CtnConfig)
+
+# name -> (restype, argtypes); must list every symbol include/ctn_b200.h declares (tests check it)
+SIGNATURES = {
+    "ctn_version": (c_i32, []),
+    "ctn_last_error": (ctypes.c_char_p, []),
+    "ctn_launch_count": (c_i64, []),
+    "ctn_param_tensors": (c_i32, [_P]),
+    "ctn_param_floats": (c_i64, [_P]),
+    "ctn_param_layout": (c_i32, [_P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32]),
+    "ctn_num_frames": (c_i32, [_P, c_i32]),
+    "ctn_workspace_bytes": (c_i64, [_P, c_i32, c_i32, c_i32]),
+    "ctn_grad_bucket": (c_i32, [_P, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "ctn_model_forward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "ctn_model_backward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "ctn_model_backward_stage": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    "ctn_pit_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "ctn_pit_forward": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_pit_backward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_reorder_source": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    "ctn_overlap_and_add": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_clip_grad_norm": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "ctn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "ctn_encoder_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_encoder_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_row_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "ctn_conv1x1": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                            c_vp, c_vp, c_vp]),
+    "ctn_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_prep_normfold": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_dwconv_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                               c_vp, c_vp, c_vp, c_vp]),
+    "ctn_dwconv_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_norm_bwd_reduce": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_norm_bwd_apply": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_decoder_fwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_decoder_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp,
+                                c_vp, c_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: the CUDA extension is not built (run `python -m conv_tasnet_b200.build`). "
+                "conv_tasnet_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libctn_b200: " + lib().ctn_last_error().decode())
+
+
+def ptr(t):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("conv_tasnet_b200 runs on CUDA tensors only (there is no CPU path); got a CPU tensor")
+    if not t.is_contiguous():
+        raise RuntimeError("internal error: non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_config(N, L, B, H, P, X, R, C, norm_type, causal, mask_nonlinear):
+    norm = {"gLN": 0, "cLN": 1}.get(norm_type)
+    if norm is None:
+        raise NotImplementedError(
+            f"norm_type={norm_type!r}: only 'gLN' and 'cLN' are on the B200 hot path (the reference's BatchNorm "
+            "fall-through, src/conv_tasnet.py:306-309, is out of scope)")
+    mask = {"relu": 0, "softmax": 1}.get(mask_nonlinear, -1)
+    return CtnConfig(N, L, B, H, P, X, R, C, norm, 1 if causal else 0, mask)

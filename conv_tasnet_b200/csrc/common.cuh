@@ -1,0 +1,131 @@
+// common.cuh — shared device helpers for the sm_100a Conv-TasNet kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ctn_b200.h"
+
+#define CTN_EPS 1e-8f
+
+namespace ctn {
+
+// ---- host-side error plumbing -----------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> 0 / 1 (+ message)
+
+#define CTN_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::ctn::set_error(__VA_ARGS__);           \
+      return 1;                                \
+    }                                          \
+  } while (0)
+
+#define CTN_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::ctn::set_error("%s failed: %s", #call, cudaGetErrorString(e__));            \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+
+#define CTN_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- normalisation statistics -----------------------------------------------------------
+// gLN: per-sample (sum, sumsq) accumulated in fp64 by the producing kernel; consumers derive
+//      mean / rstd on the fly (no finalize kernel).  cLN: per-frame (mean, rstd) floats.
+struct NormStats {
+  const double* acc;  // [M][2] or nullptr
+  const float* row;   // [F][2] or nullptr
+  double inv_count;   // 1 / (K * Ch) for gLN
+};
+
+__device__ __forceinline__ void load_stats(const NormStats& s, int m, int64_t f, float& mu, float& r) {
+  if (s.row != nullptr) {
+    float2 v = reinterpret_cast<const float2*>(s.row)[f];
+    mu = v.x;
+    r = v.y;
+  } else {
+    double S = s.acc[2 * m], S2 = s.acc[2 * m + 1];
+    double mean = S * s.inv_count;
+    double var = S2 * s.inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    mu = (float)mean;
+    r = (float)(1.0 / sqrt(var + 1e-8));
+  }
+}
+
+__device__ __forceinline__ float prelu(float z, float a) { return z > 0.f ? z : a * z; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of up to NV doubles; result valid in thread 0.  scratch: NV * 32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = lane < nw ? scratch[i * 32 + lane] : 0.0;
+      v[i] = warp_sum(x);
+    }
+  }
+}
+
+// ---- kernel launchers implemented across the .cu files (host) ---------------------------
+struct GemmArgs {
+  const float* A;  // [F, Kd]
+  const float* W;  // [O, Kd] (w_is_kn = 0) or [Kd, O] (w_is_kn = 1)
+  float* D;        // [F, O]
+  int64_t F;
+  int O, Kd, K;  // K = frames per sample (row -> sample index)
+  int w_is_kn;
+  const float* alpha_in;   // prologue PReLU slope (device scalar) or nullptr
+  const float* c1;         // norm-fold constants or nullptr
+  const float* c2;
+  NormStats st;            // stats for the norm fold
+  const float* res;        // residual [F, O] or nullptr
+  double* stat_out;        // [M][2] accumulates stats of prelu(acc, alpha_out) or nullptr
+  const float* alpha_out;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t s);
+
+struct WgradArgs {
+  const float* G;    // [F, O]
+  const float* Act;  // [F, I]
+  float* dW;         // [O, I], accumulated with atomics
+  int64_t F;
+  int O, I, K;
+  const float* alpha;  // PReLU slope or nullptr
+  const float* gamma;  // nullptr = use Act as is
+  const float* beta;
+  NormStats st;
+};
+int launch_wgrad(const WgradArgs& a, cudaStream_t s);
+
+}  // namespace ctn

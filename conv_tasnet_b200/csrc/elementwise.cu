@@ -1,0 +1,751 @@
+// elementwise.cu — the bandwidth-bound kernels of the Conv-TasNet path: encoder framing, cLN row
+// statistics, norm + dilated depthwise conv (+Chomp1d) forward/backward, gLN/cLN (+PReLU) backward,
+// mask nonlinearity + decoder basis + overlap-add forward/backward, norm-fold weight prep.
+// All activations are channels-last [M, K, Ch]; every global access is a 16-byte vector along channels.
+#include "common.cuh"
+
+namespace ctn {
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 prelu4(float4 v, float a) {
+  return make_float4(prelu(v.x, a), prelu(v.y, a), prelu(v.z, a), prelu(v.w, a));
+}
+__device__ __forceinline__ float dprelu(float z, float a) { return z > 0.f ? 1.f : a; }
+
+// ---------------------------------------------------------------------------------------
+// Encoder: w[m,k,n] = relu(sum_l U[n,l] * mix[m, k*S + l])        (src/conv_tasnet.py:119-120)
+// grid (frame tiles, M), block 256.  smem: U^T [L][N] + the tile's samples.
+// ---------------------------------------------------------------------------------------
+constexpr int ENC_TK = 16;
+__global__ void __launch_bounds__(256) encoder_fwd_kernel(const float* __restrict__ mix, const float* __restrict__ U,
+                                                          int T, int K, int N, int L, float* __restrict__ w) {
+  extern __shared__ float sm[];
+  float* Ut = sm;           // [L][N]
+  float* xs = sm + L * N;   // [ENC_TK*S + L]
+  const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENC_TK;
+  const int nk = min(ENC_TK, K - k0);
+  for (int i = threadIdx.x; i < N * L; i += blockDim.x) {
+    const int n = i / L, l = i - n * L;
+    Ut[l * N + n] = U[i];
+  }
+  const int nx = (nk - 1) * S + L;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = mix[(int64_t)m * T + (int64_t)k0 * S + i];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int k = 0; k < nk; ++k) {
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l) acc = fmaf(Ut[l * N + n], xs[k * S + l], acc);
+      w[((int64_t)m * K + k0 + k) * N + n] = fmaxf(acc, 0.f);
+    }
+  }
+}
+
+// dU[n,l] += sum_{f in tile} (dwa+dwb)[f,n] * [w[f,n] > 0] * mix[m, k*S+l]
+constexpr int ENCB_TK = 32;
+__global__ void __launch_bounds__(256) encoder_bwd_kernel(const float* __restrict__ mix, const float* __restrict__ w,
+                                                          const float* __restrict__ dwa, const float* __restrict__ dwb,
+                                                          int T, int K, int N, int L, float* __restrict__ dU) {
+  extern __shared__ float sm[];
+  float* acc = sm;          // [L][N]
+  float* xs = sm + L * N;   // [ENCB_TK*S + L]
+  const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENCB_TK;
+  const int nk = min(ENCB_TK, K - k0);
+  for (int i = threadIdx.x; i < N * L; i += blockDim.x) acc[i] = 0.f;
+  const int nx = (nk - 1) * S + L;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = mix[(int64_t)m * T + (int64_t)k0 * S + i];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int k = 0; k < nk; ++k) {
+      const int64_t idx = ((int64_t)m * K + k0 + k) * N + n;
+      float g = dwa[idx];
+      if (dwb != nullptr) g += dwb[idx];
+      if (!(w[idx] > 0.f)) g = 0.f;
+      for (int l = 0; l < L; ++l) acc[l * N + n] = fmaf(g, xs[k * S + l], acc[l * N + n]);
+    }
+    for (int l = 0; l < L; ++l) atomicAdd(dU + n * L + l, acc[l * N + n]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// cLN statistics: one warp per frame, two-pass like torch.var (src/conv_tasnet.py:332-333)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                                        int64_t F, int Ch, float* __restrict__ rowstat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const bool hasp = alpha != nullptr;
+  const float a = hasp ? __ldg(alpha) : 1.f;
+  const float* row = x + f * Ch;
+  float s = 0.f;
+  for (int c = lane * 4; c < Ch; c += 128) {
+    float4 v = ld4(row + c);
+    if (hasp) v = prelu4(v, a);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mu = warp_sum(s) / (float)Ch;
+  float q = 0.f;
+  for (int c = lane * 4; c < Ch; c += 128) {
+    float4 v = ld4(row + c);
+    if (hasp) v = prelu4(v, a);
+    const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float var = warp_sum(q) / (float)Ch;
+  if (lane == 0) {
+    rowstat[2 * f] = mu;
+    rowstat[2 * f + 1] = 1.f / sqrtf(var + CTN_EPS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// norm-fold constants: Wg = W*gamma, c1 = W@beta, c2 = rowsum(Wg).  One warp per output row.
+// Batched over `nb` convs that sit at a constant stride in the flat parameter buffer.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_normfold_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int O, int I,
+                                                            int64_t in_stride, float* __restrict__ Wg,
+                                                            float* __restrict__ c1, float* __restrict__ c2,
+                                                            int64_t wg_stride, int64_t c_stride) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  const int64_t b = blockIdx.y;
+  const float* w = W + b * in_stride + (int64_t)o * I;
+  const float* g = gamma + b * in_stride;
+  const float* be = beta + b * in_stride;
+  float* wg = Wg + b * wg_stride + (int64_t)o * I;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = lane; i < I; i += 32) {
+    const float wv = w[i], v = wv * g[i];
+    wg[i] = v;
+    s1 += (double)wv * (double)be[i];
+    s2 += (double)v;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    c1[b * c_stride + o] = (float)s1;
+    c2[b * c_stride + o] = (float)s2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// norm1 apply + dilated depthwise conv (+Chomp1d) (+ gLN stats of prelu(z2))
+// grid (frame tiles, M), block = H/4 threads rounded up to a warp (<= 256, loops over channel groups)
+// ---------------------------------------------------------------------------------------
+constexpr int DW_TK = 8;
+constexpr int MAXP = 8;
+
+template <int PT>
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ alpha1,
+                                                         NormStats st1, const float* __restrict__ gamma1,
+                                                         const float* __restrict__ beta1, const float* __restrict__ Wd,
+                                                         int K, int H, int P, int dil, int cshift,
+                                                         float* __restrict__ z2, double* __restrict__ stat_out,
+                                                         const float* __restrict__ alpha2) {
+  __shared__ double red[2 * 32];
+  __shared__ float2 s_st;
+  const int m = blockIdx.y, k0 = blockIdx.x * DW_TK;
+  const int nk = min(DW_TK, K - k0);
+  if (st1.row == nullptr) {
+    if (threadIdx.x == 0) {
+      float mu, r;
+      load_stats(st1, m, 0, mu, r);
+      s_st = make_float2(mu, r);
+    }
+    __syncthreads();
+  }
+  const float a1 = __ldg(alpha1);
+  const bool do_stats = stat_out != nullptr;
+  const float a2 = do_stats ? __ldg(alpha2) : 1.f;
+  const int64_t base = (int64_t)m * K;
+  double acc[2] = {0.0, 0.0};
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
+    constexpr int NP_ = PT ? PT : MAXP;
+    const int PP = PT ? PT : P;
+    float wd[4][NP_];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int p = 0; p < NP_; ++p) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
+    float s = 0.f, s2 = 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int k = k0 + kk;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < NP_; ++p) {
+        const int ks = k + (p - cshift) * dil;
+        if (p >= PP || ks < 0 || ks >= K) continue;  // zero padding is applied after the norm
+        float mu, r;
+        if (st1.row != nullptr) {
+          const float2 v = reinterpret_cast<const float2*>(st1.row)[base + ks];
+          mu = v.x; r = v.y;
+        } else {
+          mu = s_st.x; r = s_st.y;
+        }
+        float4 v = prelu4(ld4(z1 + (base + ks) * H + c), a1);
+        o.x = fmaf(wd[0][p], g.x * (v.x - mu) * r + b.x, o.x);
+        o.y = fmaf(wd[1][p], g.y * (v.y - mu) * r + b.y, o.y);
+        o.z = fmaf(wd[2][p], g.z * (v.z - mu) * r + b.z, o.z);
+        o.w = fmaf(wd[3][p], g.w * (v.w - mu) * r + b.w, o.w);
+      }
+      st4(z2 + (base + k) * H + c, o);
+      if (do_stats) {
+        const float4 q = prelu4(o, a2);
+        s += (q.x + q.y) + (q.z + q.w);
+        s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+      }
+    }
+    acc[0] += (double)s;
+    acc[1] += (double)s2;
+  }
+  if (do_stats) {
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(stat_out + 2 * m, acc[0]);
+      atomicAdd(stat_out + 2 * m + 1, acc[1]);
+    }
+  }
+}
+
+// backward: dn1[k] = sum_p Wd[p] * dz2[k - off_p];  dWd[p] += dz2[k - off_p] * n1[k];
+// plus the per-channel / per-sample reductions the norm1 backward needs (dgamma1, dbeta1, red1).
+constexpr int DWB_TK = 16;
+template <int PT>
+__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict__ dz2, const float* __restrict__ z1,
+                                                         const float* __restrict__ alpha1, NormStats st1,
+                                                         const float* __restrict__ gamma1, const float* __restrict__ beta1,
+                                                         const float* __restrict__ Wd, int K, int H, int P, int dil,
+                                                         int cshift, float* __restrict__ dn1, float* __restrict__ dWd,
+                                                         float* __restrict__ dgamma1, float* __restrict__ dbeta1,
+                                                         double* __restrict__ red1) {
+  __shared__ double red[2 * 32];
+  __shared__ float2 s_st;
+  const int m = blockIdx.y, k0 = blockIdx.x * DWB_TK;
+  const int nk = min(DWB_TK, K - k0);
+  if (st1.row == nullptr) {
+    if (threadIdx.x == 0) {
+      float mu, r;
+      load_stats(st1, m, 0, mu, r);
+      s_st = make_float2(mu, r);
+    }
+    __syncthreads();
+  }
+  const float a1 = __ldg(alpha1);
+  const int64_t base = (int64_t)m * K;
+  double acc[2] = {0.0, 0.0};
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
+    constexpr int NP_ = PT ? PT : MAXP;
+    const int PP = PT ? PT : P;
+    float wd[4][NP_], dwd[4][NP_];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int p = 0; p < NP_; ++p) {
+        wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
+        dwd[j][p] = 0.f;
+      }
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+    float s = 0.f, s2 = 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int k = k0 + kk;
+      float mu, r;
+      if (st1.row != nullptr) {
+        const float2 v = reinterpret_cast<const float2*>(st1.row)[base + k];
+        mu = v.x; r = v.y;
+      } else {
+        mu = s_st.x; r = s_st.y;
+      }
+      const float4 a = prelu4(ld4(z1 + (base + k) * H + c), a1);
+      const float4 yh = make_float4((a.x - mu) * r, (a.y - mu) * r, (a.z - mu) * r, (a.w - mu) * r);
+      const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < NP_; ++p) {
+        const int ko = k - (p - cshift) * dil;  // the output frame whose tap p read input frame k
+        if (p >= PP || ko < 0 || ko >= K) continue;
+        const float4 v = ld4(dz2 + (base + ko) * H + c);
+        d.x = fmaf(wd[0][p], v.x, d.x); d.y = fmaf(wd[1][p], v.y, d.y);
+        d.z = fmaf(wd[2][p], v.z, d.z); d.w = fmaf(wd[3][p], v.w, d.w);
+        dwd[0][p] = fmaf(v.x, n1.x, dwd[0][p]); dwd[1][p] = fmaf(v.y, n1.y, dwd[1][p]);
+        dwd[2][p] = fmaf(v.z, n1.z, dwd[2][p]); dwd[3][p] = fmaf(v.w, n1.w, dwd[3][p]);
+      }
+      st4(dn1 + (base + k) * H + c, d);
+      dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+      dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+      const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s += (gh.x + gh.y) + (gh.z + gh.w);
+      s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int p = 0; p < NP_; ++p)
+        if (p < PP) atomicAdd(dWd + (c + j) * PP + p, dwd[j][p]);
+    atomicAdd(dgamma1 + c + 0, dg.x); atomicAdd(dgamma1 + c + 1, dg.y);
+    atomicAdd(dgamma1 + c + 2, dg.z); atomicAdd(dgamma1 + c + 3, dg.w);
+    atomicAdd(dbeta1 + c + 0, db.x); atomicAdd(dbeta1 + c + 1, db.y);
+    atomicAdd(dbeta1 + c + 2, db.z); atomicAdd(dbeta1 + c + 3, db.w);
+    acc[0] += (double)s;
+    acc[1] += (double)s2;
+  }
+  if (red1 != nullptr) {
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(red1 + 2 * m, acc[0]);
+      atomicAdd(red1 + 2 * m + 1, acc[1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// norm backward, reduction pass: dgamma[c] += sum dn*yhat, dbeta[c] += sum dn,
+// red[m] += (sum dn*gamma, sum dn*gamma*yhat)
+// ---------------------------------------------------------------------------------------
+constexpr int NR_TK = 32;
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ dn, const float* __restrict__ z,
+                                                              const float* __restrict__ alpha, NormStats st,
+                                                              const float* __restrict__ gamma, int K, int Ch,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              double* __restrict__ redout) {
+  __shared__ double red[2 * 32];
+  __shared__ float2 s_st;
+  const int m = blockIdx.y, k0 = blockIdx.x * NR_TK;
+  const int nk = min(NR_TK, K - k0);
+  if (st.row == nullptr) {
+    if (threadIdx.x == 0) {
+      float mu, r;
+      load_stats(st, m, 0, mu, r);
+      s_st = make_float2(mu, r);
+    }
+    __syncthreads();
+  }
+  const bool hasp = alpha != nullptr;
+  const float a = hasp ? __ldg(alpha) : 1.f;
+  const int64_t base = (int64_t)m * K;
+  double acc[2] = {0.0, 0.0};
+  for (int c = threadIdx.x * 4; c < Ch; c += blockDim.x * 4) {
+    const float4 g = ld4(gamma + c);
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+    float s = 0.f, s2 = 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int64_t f = base + k0 + kk;
+      float mu, r;
+      if (st.row != nullptr) {
+        const float2 v = reinterpret_cast<const float2*>(st.row)[f];
+        mu = v.x; r = v.y;
+      } else {
+        mu = s_st.x; r = s_st.y;
+      }
+      float4 v = ld4(z + f * Ch + c);
+      if (hasp) v = prelu4(v, a);
+      const float4 d = ld4(dn + f * Ch + c);
+      const float4 yh = make_float4((v.x - mu) * r, (v.y - mu) * r, (v.z - mu) * r, (v.w - mu) * r);
+      dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+      dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+      const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s += (gh.x + gh.y) + (gh.z + gh.w);
+      s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+    }
+    atomicAdd(dgamma + c + 0, dg.x); atomicAdd(dgamma + c + 1, dg.y);
+    atomicAdd(dgamma + c + 2, dg.z); atomicAdd(dgamma + c + 3, dg.w);
+    atomicAdd(dbeta + c + 0, db.x); atomicAdd(dbeta + c + 1, db.y);
+    atomicAdd(dbeta + c + 2, db.z); atomicAdd(dbeta + c + 3, db.w);
+    acc[0] += (double)s;
+    acc[1] += (double)s2;
+  }
+  if (redout != nullptr) {
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(redout + 2 * m, acc[0]);
+      atomicAdd(redout + 2 * m + 1, acc[1]);
+    }
+  }
+}
+
+// apply pass, gLN: dz = r*(dn*gamma - m1 - yhat*m2) * prelu'(z); dalpha += sum da * z * [z<=0]
+__global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
+                                                            const float* __restrict__ alpha, NormStats st,
+                                                            const float* __restrict__ gamma, const double* __restrict__ redin,
+                                                            int K, int Ch, float* __restrict__ dalpha) {
+  __shared__ double red[32];
+  __shared__ float4 s_st;
+  const int m = blockIdx.y, k0 = blockIdx.x * NR_TK;
+  const int nk = min(NR_TK, K - k0);
+  if (threadIdx.x == 0) {
+    float mu, r;
+    load_stats(st, m, 0, mu, r);
+    const double cnt = (double)K * (double)Ch;
+    s_st = make_float4(mu, r, (float)(redin[2 * m] / cnt), (float)(redin[2 * m + 1] / cnt));
+  }
+  __syncthreads();
+  const float mu = s_st.x, r = s_st.y, m1 = s_st.z, m2 = s_st.w;
+  const bool hasp = alpha != nullptr;
+  const float a = hasp ? __ldg(alpha) : 1.f;
+  const int64_t base = (int64_t)m * K;
+  double acc[1] = {0.0};
+  for (int c = threadIdx.x * 4; c < Ch; c += blockDim.x * 4) {
+    const float4 g = ld4(gamma + c);
+    float s = 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int64_t f = base + k0 + kk;
+      const float4 zz = ld4(z + f * Ch + c);
+      const float4 v = hasp ? prelu4(zz, a) : zz;
+      const float4 d = ld4(dn + f * Ch + c);
+      float4 da;
+      da.x = r * (d.x * g.x - m1 - (v.x - mu) * r * m2);
+      da.y = r * (d.y * g.y - m1 - (v.y - mu) * r * m2);
+      da.z = r * (d.z * g.z - m1 - (v.z - mu) * r * m2);
+      da.w = r * (d.w * g.w - m1 - (v.w - mu) * r * m2);
+      if (hasp) {
+        s += (zz.x > 0.f ? 0.f : da.x * zz.x) + (zz.y > 0.f ? 0.f : da.y * zz.y) +
+             (zz.z > 0.f ? 0.f : da.z * zz.z) + (zz.w > 0.f ? 0.f : da.w * zz.w);
+        da.x *= dprelu(zz.x, a); da.y *= dprelu(zz.y, a); da.z *= dprelu(zz.z, a); da.w *= dprelu(zz.w, a);
+      }
+      st4(dn + f * Ch + c, da);
+    }
+    acc[0] += (double)s;
+  }
+  if (hasp) {
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, (float)acc[0]);
+  }
+}
+
+// apply pass, cLN: one warp per frame (means over channels inside the warp)
+__global__ void __launch_bounds__(256) cln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
+                                                            const float* __restrict__ alpha, const float* __restrict__ rowstat,
+                                                            const float* __restrict__ gamma, int64_t F, int Ch,
+                                                            float* __restrict__ dalpha) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool hasp = alpha != nullptr;
+  const float a = hasp ? __ldg(alpha) : 1.f;
+  float sa = 0.f;
+  if (f < F) {
+    const float mu = rowstat[2 * f], r = rowstat[2 * f + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane * 4; c < Ch; c += 128) {
+      const float4 g = ld4(gamma + c), d = ld4(dn + f * Ch + c);
+      float4 v = ld4(z + f * Ch + c);
+      if (hasp) v = prelu4(v, a);
+      const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s1 += (gh.x + gh.y) + (gh.z + gh.w);
+      s2 += gh.x * (v.x - mu) * r + gh.y * (v.y - mu) * r + gh.z * (v.z - mu) * r + gh.w * (v.w - mu) * r;
+    }
+    const float m1 = warp_sum(s1) / (float)Ch, m2 = warp_sum(s2) / (float)Ch;
+    for (int c = lane * 4; c < Ch; c += 128) {
+      const float4 g = ld4(gamma + c), d = ld4(dn + f * Ch + c);
+      const float4 zz = ld4(z + f * Ch + c);
+      const float4 v = hasp ? prelu4(zz, a) : zz;
+      float4 da;
+      da.x = r * (d.x * g.x - m1 - (v.x - mu) * r * m2);
+      da.y = r * (d.y * g.y - m1 - (v.y - mu) * r * m2);
+      da.z = r * (d.z * g.z - m1 - (v.z - mu) * r * m2);
+      da.w = r * (d.w * g.w - m1 - (v.w - mu) * r * m2);
+      if (hasp) {
+        sa += (zz.x > 0.f ? 0.f : da.x * zz.x) + (zz.y > 0.f ? 0.f : da.y * zz.y) +
+              (zz.z > 0.f ? 0.f : da.z * zz.z) + (zz.w > 0.f ? 0.f : da.w * zz.w);
+        da.x *= dprelu(zz.x, a); da.y *= dprelu(zz.y, a); da.z *= dprelu(zz.z, a); da.w *= dprelu(zz.w, a);
+      }
+      st4(dn + f * Ch + c, da);
+    }
+  }
+  if (hasp) {
+    double acc[1] = {(double)sa};
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, (float)acc[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Decoder forward: mask nonlinearity, * w, basis V, overlap-add with step S = L/2, zero pad to T.
+// grid (frame tiles, M); one warp per frame computes frames[k][c][l]; then the block writes its
+// span of output samples (each sample sums the <= ceil(L/S) frames that cover it, ascending k).
+// ---------------------------------------------------------------------------------------
+constexpr int DEC_TK = 32;
+constexpr int MAXC = 4;
+__global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ score, const float* __restrict__ w,
+                                                          const float* __restrict__ V, int K, int C, int N, int L,
+                                                          int T, int softmax, float* __restrict__ est) {
+  extern __shared__ float sm[];
+  const int S = L / 2;
+  const int halo = (L - 1) / S;  // frames before the tile that still reach into it
+  const int NP = N + 1;          // padded row: lanes with different l hit different banks
+  float* Vs = sm;                               // [L][N+1]
+  float* fr = Vs + L * NP;                      // [(DEC_TK + halo)][C][L]
+  float* sws = fr + (DEC_TK + halo) * C * L;    // [warps][C][N]  masked mixture weights of the warp's frame
+  const int m = blockIdx.y, k0 = blockIdx.x * DEC_TK;
+  const int kb = max(0, k0 - halo), ke = min(K, k0 + DEC_TK);
+  for (int i = threadIdx.x; i < L * N; i += blockDim.x) Vs[(i / N) * NP + (i % N)] = V[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* sw = sws + wid * C * N;
+  for (int k = kb + wid; k < ke; k += nw) {
+    const int64_t f = (int64_t)m * K + k;
+    for (int n = lane; n < N; n += 32) {
+      const float wv = w[f * N + n];
+      float sc[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) sc[c] = c < C ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
+      if (softmax) {
+        float mx = sc[0];
+#pragma unroll
+        for (int c = 1; c < MAXC; ++c) mx = fmaxf(mx, sc[c]);
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) { sc[c] = c < C ? expf(sc[c] - mx) : 0.f; den += sc[c]; }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) sc[c] = sc[c] / den * wv;
+      } else {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) sc[c] = fmaxf(sc[c], 0.f) * wv;
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < C) sw[c * N + n] = sc[c];
+    }
+    __syncwarp();
+    float* out = fr + (k - kb) * C * L;
+    for (int i = lane; i < C * L; i += 32) {
+      const int c = i / L, l = i - c * L;
+      const float* swc = sw + c * N;
+      const float* vl = Vs + l * NP;
+      float acc = 0.f;
+      for (int n = 0; n < N; ++n) acc = fmaf(swc[n], vl[n], acc);
+      out[i] = acc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // output span of this tile: [k0*S, (k0+DEC_TK)*S), the last tile runs to T (tail + zero pad)
+  const int t0 = k0 * S;
+  const int t1 = (k0 + DEC_TK >= K) ? T : (k0 + DEC_TK) * S;
+  for (int c = 0; c < C; ++c) {
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+      float acc = 0.f;
+      const int khi = min(t / S, K - 1);
+      int klo = (t - L + S) / S;  // ceil((t-L+1)/S) for t-L+1 >= 0
+      if (t - L + 1 <= 0) klo = 0;
+      for (int k = max(klo, kb); k <= khi; ++k) {
+        const int l = t - k * S;
+        if (l >= 0 && l < L) acc += fr[((k - kb) * C + c) * L + l];
+      }
+      est[((int64_t)m * C + c) * T + t] = acc;
+    }
+  }
+}
+
+// Decoder backward: thread per basis channel n, loop over the tile's frames.
+constexpr int DECB_TK = 32;
+__global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restrict__ d_est, const float* __restrict__ score,
+                                                          const float* __restrict__ w, const float* __restrict__ V, int K,
+                                                          int C, int N, int L, int T, int softmax,
+                                                          float* __restrict__ d_score, float* __restrict__ d_w,
+                                                          float* __restrict__ dV) {
+  extern __shared__ float sm[];
+  const int S = L / 2;
+  float* Vs = sm;                 // [L][N]
+  float* dVs = sm + L * N;        // [L][N]
+  float* df = sm + 2 * L * N;     // [DECB_TK][C][L]
+  const int m = blockIdx.y, k0 = blockIdx.x * DECB_TK;
+  const int nk = min(DECB_TK, K - k0);
+  for (int i = threadIdx.x; i < L * N; i += blockDim.x) { Vs[i] = V[i]; dVs[i] = 0.f; }
+  for (int i = threadIdx.x; i < nk * C * L; i += blockDim.x) {
+    const int l = i % L, c = (i / L) % C, kk = i / (L * C);
+    df[i] = d_est[((int64_t)m * C + c) * T + (int64_t)(k0 + kk) * S + l];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int kk = 0; kk < nk; ++kk) {
+      const int64_t f = (int64_t)m * K + k0 + kk;
+      const float wv = w[f * N + n];
+      float sc[MAXC], mk[MAXC], dsw[MAXC];
+      for (int c = 0; c < C; ++c) sc[c] = score[f * (int64_t)(C * N) + c * N + n];
+      if (softmax) {
+        float mx = sc[0];
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, sc[c]);
+        float den = 0.f;
+        for (int c = 0; c < C; ++c) { mk[c] = expf(sc[c] - mx); den += mk[c]; }
+        for (int c = 0; c < C; ++c) mk[c] /= den;
+      } else {
+        for (int c = 0; c < C; ++c) mk[c] = fmaxf(sc[c], 0.f);
+      }
+      float dwv = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float* dfc = df + (kk * C + c) * L;
+        const float sw = mk[c] * wv;
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l) {
+          acc = fmaf(dfc[l], Vs[l * N + n], acc);
+          dVs[l * N + n] = fmaf(dfc[l], sw, dVs[l * N + n]);
+        }
+        dsw[c] = acc;
+        dwv = fmaf(acc, mk[c], dwv);
+      }
+      d_w[f * N + n] = dwv;
+      if (softmax) {
+        float dot = 0.f;
+        for (int c = 0; c < C; ++c) dot = fmaf(dsw[c] * wv, mk[c], dot);
+        for (int c = 0; c < C; ++c) d_score[f * (int64_t)(C * N) + c * N + n] = mk[c] * (dsw[c] * wv - dot);
+      } else {
+        for (int c = 0; c < C; ++c) d_score[f * (int64_t)(C * N) + c * N + n] = sc[c] > 0.f ? dsw[c] * wv : 0.f;
+      }
+    }
+    for (int l = 0; l < L; ++l) atomicAdd(dV + l * N + n, dVs[l * N + n]);
+  }
+}
+
+// utils.overlap_and_add as a standalone op: out[o, t] = sum_k sig[o, k, t - k*step], ascending k
+__global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ sig, int frames, int flen, int step,
+                                                  int64_t out_len, float* __restrict__ out) {
+  const int64_t o = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= out_len) return;
+  int64_t khi = t / step;
+  if (khi > frames - 1) khi = frames - 1;
+  int64_t klo = t - flen + 1 <= 0 ? 0 : (t - flen + step) / step;
+  float acc = 0.f;
+  for (int64_t k = klo; k <= khi; ++k) acc += sig[(o * frames + k) * flen + (t - k * step)];
+  out[o * out_len + t] = acc;
+}
+
+static int block_for_channels(int Ch) {
+  int t = ((Ch / 4 + 31) / 32) * 32;
+  return t > 256 ? 256 : (t < 32 ? 32 : t);
+}
+
+static int ensure_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    CTN_REQUIRE(bytes <= 227 * 1024, "kernel needs %zu bytes of shared memory (> 227 KB): N*L too large", bytes);
+    CTN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host launchers (C linkage wrappers live in c_api.cu)
+// ---------------------------------------------------------------------------------------
+int run_encoder_fwd(const float* mix, const float* U, int M, int T, int N, int L, float* w, cudaStream_t s) {
+  CTN_REQUIRE(L >= 2 && T >= L, "encoder: need L >= 2 and T >= L (T=%d L=%d)", T, L);
+  const int S = L / 2, K = (T - L) / S + 1;
+  const size_t smem = (size_t)(L * N + ENC_TK * S + L) * sizeof(float);
+  CTN_TRY(ensure_smem((const void*)encoder_fwd_kernel, smem));
+  encoder_fwd_kernel<<<dim3(cdiv(K, ENC_TK), M), 256, smem, s>>>(mix, U, T, K, N, L, w);
+  return check_launch("encoder_fwd_kernel");
+}
+
+int run_encoder_bwd(const float* mix, const float* w, const float* dwa, const float* dwb, int M, int T, int N, int L,
+                    float* dU, cudaStream_t s) {
+  const int S = L / 2, K = (T - L) / S + 1;
+  const size_t smem = (size_t)(L * N + ENCB_TK * S + L) * sizeof(float);
+  CTN_TRY(ensure_smem((const void*)encoder_bwd_kernel, smem));
+  encoder_bwd_kernel<<<dim3(cdiv(K, ENCB_TK), M), 256, smem, s>>>(mix, w, dwa, dwb, T, K, N, L, dU);
+  return check_launch("encoder_bwd_kernel");
+}
+
+int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s) {
+  CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
+  row_stats_kernel<<<cdiv(F, 8), 256, 0, s>>>(x, alpha, F, Ch, rowstat);
+  return check_launch("row_stats_kernel");
+}
+
+int run_prep_normfold(const float* W, const float* gamma, const float* beta, int O, int I, int nb, int64_t in_stride,
+                      float* Wg, float* c1, float* c2, int64_t wg_stride, int64_t c_stride, cudaStream_t s) {
+  prep_normfold_kernel<<<dim3(cdiv(O, 8), nb), 256, 0, s>>>(W, gamma, beta, O, I, in_stride, Wg, c1, c2, wg_stride,
+                                                            c_stride);
+  return check_launch("prep_normfold_kernel");
+}
+
+int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const float* gamma1, const float* beta1,
+                   const float* Wd, int M, int K, int H, int P, int dil, int causal, float* z2, double* stat_out,
+                   const float* alpha2, cudaStream_t s) {
+  CTN_REQUIRE(H % 4 == 0, "dwconv: H must be a multiple of 4 (got %d)", H);
+  CTN_REQUIRE(P >= 1 && P <= MAXP, "dwconv: kernel size P must be in [1,%d] (got %d)", MAXP, P);
+  CTN_REQUIRE(causal || (P % 2 == 1), "dwconv: non-causal needs odd P (reference output length changes otherwise)");
+  const int cshift = causal ? P - 1 : (P - 1) / 2;
+  const dim3 grid(cdiv(K, DW_TK), M);
+  if (P == 3)
+    dwconv_fwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift,
+                                                               z2, stat_out, alpha2);
+  else
+    dwconv_fwd_kernel<0><<<grid, block_for_channels(H), 0, s>>>(z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift,
+                                                               z2, stat_out, alpha2);
+  return check_launch("dwconv_fwd_kernel");
+}
+
+int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormStats st1, const float* gamma1,
+                   const float* beta1, const float* Wd, int M, int K, int H, int P, int dil, int causal, float* dn1,
+                   float* dWd, float* dgamma1, float* dbeta1, double* red1, cudaStream_t s) {
+  CTN_REQUIRE(H % 4 == 0 && P >= 1 && P <= MAXP, "dwconv_bwd: bad H/P (%d/%d)", H, P);
+  const int cshift = causal ? P - 1 : (P - 1) / 2;
+  const dim3 grid(cdiv(K, DWB_TK), M);
+  if (P == 3)
+    dwconv_bwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
+                                                               cshift, dn1, dWd, dgamma1, dbeta1, red1);
+  else
+    dwconv_bwd_kernel<0><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
+                                                               cshift, dn1, dWd, dgamma1, dbeta1, red1);
+  return check_launch("dwconv_bwd_kernel");
+}
+
+int run_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, NormStats st, const float* gamma, int M,
+                        int K, int Ch, float* dgamma, float* dbeta, double* red, cudaStream_t s) {
+  CTN_REQUIRE(Ch % 4 == 0, "norm_bwd: channels must be a multiple of 4 (got %d)", Ch);
+  norm_bwd_reduce_kernel<<<dim3(cdiv(K, NR_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, K, Ch,
+                                                                                   dgamma, dbeta, red);
+  return check_launch("norm_bwd_reduce_kernel");
+}
+
+int run_norm_bwd_apply(float* dn, const float* z, const float* alpha, NormStats st, const float* gamma,
+                       const double* red, int M, int K, int Ch, float* dalpha, cudaStream_t s) {
+  CTN_REQUIRE(Ch % 4 == 0, "norm_bwd: channels must be a multiple of 4 (got %d)", Ch);
+  if (st.row != nullptr) {
+    cln_bwd_apply_kernel<<<cdiv((int64_t)M * K, 8), 256, 0, s>>>(dn, z, alpha, st.row, gamma, (int64_t)M * K, Ch,
+                                                               dalpha);
+    return check_launch("cln_bwd_apply_kernel");
+  }
+  gln_bwd_apply_kernel<<<dim3(cdiv(K, NR_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, red, K, Ch,
+                                                                                 dalpha);
+  return check_launch("gln_bwd_apply_kernel");
+}
+
+int run_decoder_fwd(const float* score, const float* w, const float* V, int M, int K, int C, int N, int L, int T,
+                    int softmax, float* est, cudaStream_t s) {
+  CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
+  const int S = L / 2, halo = (L - 1) / S;
+  const size_t smem = (size_t)(L * (N + 1) + (DEC_TK + halo) * C * L + 8 * C * N) * sizeof(float);
+  CTN_TRY(ensure_smem((const void*)decoder_fwd_kernel, smem));
+  decoder_fwd_kernel<<<dim3(cdiv(K, DEC_TK), M), 256, smem, s>>>(score, w, V, K, C, N, L, T, softmax, est);
+  return check_launch("decoder_fwd_kernel");
+}
+
+int run_decoder_bwd(const float* d_est, const float* score, const float* w, const float* V, int M, int K, int C, int N,
+                    int L, int T, int softmax, float* d_score, float* d_w, float* dV, cudaStream_t s) {
+  CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
+  const size_t smem = (size_t)(2 * L * N + DECB_TK * C * L) * sizeof(float);
+  CTN_TRY(ensure_smem((const void*)decoder_bwd_kernel, smem));
+  decoder_bwd_kernel<<<dim3(cdiv(K, DECB_TK), M), 256, smem, s>>>(d_est, score, w, V, K, C, N, L, T, softmax, d_score,
+                                                                 d_w, dV);
+  return check_launch("decoder_bwd_kernel");
+}
+
+int run_overlap_and_add(const float* sig, int64_t outer, int frames, int flen, int step, float* out, cudaStream_t s) {
+  CTN_REQUIRE(step >= 1 && step <= flen, "overlap_and_add: frame_step must be in [1, frame_length]");
+  CTN_REQUIRE(outer <= 65535, "overlap_and_add: too many outer rows (%lld)", (long long)outer);
+  const int64_t out_len = (int64_t)(frames - 1) * step + flen;
+  ola_kernel<<<dim3(cdiv(out_len, 256), (unsigned)outer), 256, 0, s>>>(sig, frames, flen, step, out_len, out);
+  return check_launch("ola_kernel");
+}
+
+}  // namespace ctn

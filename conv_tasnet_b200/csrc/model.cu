@@ -1,0 +1,459 @@
+// model.cu — parameter/workspace geometry and the whole-path orchestration:
+// ConvTasNet.forward (src/conv_tasnet.py:45-60) and its hand-written backward, as a fixed sequence
+// of kernel launches on one stream (graph-capturable: no allocation, no host sync, no host-side
+// data-dependent control flow).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ctn {
+
+// ---- error plumbing ------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+static unsigned long long g_launches = 0;  // kernels launched through this library (bench.py's gpu_launches)
+int check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// ---- launchers defined in the other translation units ---------------------------------------
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
+int launch_wgrad_simt(const WgradArgs& a, cudaStream_t s);
+int run_encoder_fwd(const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int run_encoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t);
+int run_prep_normfold(const float*, const float*, const float*, int, int, int, int64_t, float*, float*, float*, int64_t,
+                      int64_t, cudaStream_t);
+int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
+                   int, int, float*, double*, const float*, cudaStream_t);
+int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
+                   int, int, int, int, int, float*, float*, float*, float*, double*, cudaStream_t);
+int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
+                        float*, double*, cudaStream_t);
+int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
+                       float*, cudaStream_t);
+int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
+int run_decoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, float*,
+                    float*, float*, cudaStream_t);
+
+int launch_gemm(const GemmArgs& a, cudaStream_t s) { return launch_gemm_simt(a, s); }
+int launch_wgrad(const WgradArgs& a, cudaStream_t s) { return launch_wgrad_simt(a, s); }
+
+// ---- flat parameter layout (reference state_dict order) -------------------------
+static inline int64_t al4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+
+struct ParamLayout {
+  int64_t U, g0, b0, Wb, blk0, blk_stride, Wm, V, total;
+  int64_t W1, a1, g1, b1, Wd, a2, g2, b2, W2;  // offsets inside one TemporalBlock
+};
+
+static ParamLayout make_layout(const ctn_config& c) {
+  ParamLayout L;
+  int64_t o = 0;
+  L.U = o; o += al4((int64_t)c.N * c.L);
+  L.g0 = o; o += al4(c.N);
+  L.b0 = o; o += al4(c.N);
+  L.Wb = o; o += al4((int64_t)c.B * c.N);
+  L.blk0 = o;
+  int64_t q = 0;
+  L.W1 = q; q += al4((int64_t)c.H * c.B);
+  L.a1 = q; q += 4;
+  L.g1 = q; q += al4(c.H);
+  L.b1 = q; q += al4(c.H);
+  L.Wd = q; q += al4((int64_t)c.H * c.P);
+  L.a2 = q; q += 4;
+  L.g2 = q; q += al4(c.H);
+  L.b2 = q; q += al4(c.H);
+  L.W2 = q; q += al4((int64_t)c.B * c.H);
+  L.blk_stride = q;
+  o += q * c.R * c.X;
+  L.Wm = o; o += al4((int64_t)c.C * c.N * c.B);
+  L.V = o; o += al4((int64_t)c.L * c.N);
+  L.total = o;
+  return L;
+}
+
+static int validate(const ctn_config* c) {
+  CTN_REQUIRE(c != nullptr, "null config");
+  CTN_REQUIRE(c->N > 0 && c->L >= 2 && c->B > 0 && c->H > 0 && c->P > 0 && c->X > 0 && c->R > 0 && c->C > 0,
+              "config: all of N,L,B,H,P,X,R,C must be positive and L >= 2");
+  CTN_REQUIRE(c->N % 4 == 0 && c->B % 4 == 0 && c->H % 4 == 0, "config: N, B, H must be multiples of 4 (got %d,%d,%d)",
+              c->N, c->B, c->H);
+  CTN_REQUIRE(c->C <= 4, "config: C <= 4 supported (got %d)", c->C);
+  CTN_REQUIRE(c->P <= 8, "config: P <= 8 supported (got %d)", c->P);
+  CTN_REQUIRE(c->X <= 20, "config: X <= 20 (dilation 2^x)");
+  CTN_REQUIRE(c->norm_type == CTN_NORM_GLN || c->norm_type == CTN_NORM_CLN,
+              "config: norm_type must be gLN or cLN (the BatchNorm branch is outside the hot path)");
+  CTN_REQUIRE(c->causal || (c->P % 2 == 1), "config: non-causal needs odd P");
+  CTN_REQUIRE(c->mask_nonlinear == CTN_MASK_RELU || c->mask_nonlinear == CTN_MASK_SOFTMAX,
+              "Unsupported mask non-linear function");
+  return 0;
+}
+
+// ---- workspace plan --------------------------------------------------------------------------
+struct Plan {
+  int M, T, K, nblk, training;
+  int64_t F;
+  // byte offsets
+  int64_t w, rowstat0, x, z1, z2, gacc, rs1, rs2, score, Wbg, c1b, c2b, W2g, c1, c2;
+  int64_t g, dn2, dn1, d_score, d_w, dn0, red;
+  int64_t x_stride, z_stride, rs_stride;  // bytes between consecutive blocks' buffers (0 when not stashed)
+  int64_t total;
+};
+
+static inline int64_t al256(int64_t n) { return (n + 255) & ~(int64_t)255; }
+
+static Plan make_plan(const ctn_config& c, int M, int T, int training) {
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.T = T; p.training = training;
+  const int S = c.L / 2;
+  p.K = (T - c.L) / S + 1;
+  p.F = (int64_t)M * p.K;
+  p.nblk = c.R * c.X;
+  const int64_t F = p.F;
+  const bool cln = c.norm_type == CTN_NORM_CLN;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += al256(bytes); return r; };
+  p.w = take(F * c.N * 4);
+  p.rowstat0 = take(F * 2 * 4);
+  p.x_stride = al256(F * c.B * 4);
+  p.x = o; o += p.x_stride * (training ? p.nblk + 1 : 2);
+  p.z_stride = al256(F * c.H * 4);
+  p.z1 = o; o += p.z_stride * (training ? p.nblk : 1);
+  p.z2 = o; o += p.z_stride * (training ? p.nblk : 1);
+  p.gacc = take((int64_t)p.nblk * 2 * M * 2 * 8);
+  p.rs_stride = cln ? al256(F * 2 * 4) : 0;
+  p.rs1 = o; o += p.rs_stride * (training ? p.nblk : 1);
+  p.rs2 = o; o += p.rs_stride * (training ? p.nblk : 1);
+  p.score = take(F * c.C * c.N * 4);
+  p.Wbg = take((int64_t)c.B * c.N * 4);
+  p.c1b = take(c.B * 4);
+  p.c2b = take(c.B * 4);
+  p.W2g = take((int64_t)p.nblk * c.B * c.H * 4);
+  p.c1 = take((int64_t)p.nblk * c.B * 4);
+  p.c2 = take((int64_t)p.nblk * c.B * 4);
+  if (training) {
+    p.g = take(2 * al256(F * c.B * 4));
+    p.dn2 = take(F * c.H * 4);
+    p.dn1 = take(F * c.H * 4);
+    p.d_score = take(F * c.C * c.N * 4);
+    p.d_w = take(F * c.N * 4);
+    p.dn0 = take(F * c.N * 4);
+    p.red = take((int64_t)(p.nblk * 2 + 1) * M * 2 * 8);
+  }
+  p.total = o;
+  return p;
+}
+
+struct Ctx {
+  const ctn_config& c;
+  ParamLayout L;
+  Plan p;
+  const float* params;
+  char* ws;
+  cudaStream_t s;
+  template <typename T>
+  T* at(int64_t off) const { return reinterpret_cast<T*>(ws + off); }
+  const float* blk(int b, int64_t off) const { return params + L.blk0 + (int64_t)b * L.blk_stride + off; }
+  // block input b (b == nblk is the separator output)
+  float* x(int b) const { return at<float>(p.x + p.x_stride * (p.training ? b : (b & 1))); }
+  float* z1(int b) const { return at<float>(p.z1 + p.z_stride * (p.training ? b : 0)); }
+  float* z2(int b) const { return at<float>(p.z2 + p.z_stride * (p.training ? b : 0)); }
+  NormStats stats(int b, int which) const {
+    NormStats st;
+    if (c.norm_type == CTN_NORM_GLN) {
+      st.acc = at<double>(p.gacc) + ((int64_t)b * 2 + which) * p.M * 2;
+      st.row = nullptr;
+      st.inv_count = 1.0 / ((double)p.K * (double)c.H);
+    } else {
+      st.acc = nullptr;
+      st.row = at<float>((which ? p.rs2 : p.rs1) + p.rs_stride * (p.training ? b : 0));
+      st.inv_count = 0.0;
+    }
+    return st;
+  }
+  double* stat_out(int b, int which) const {
+    return c.norm_type == CTN_NORM_GLN ? at<double>(p.gacc) + ((int64_t)b * 2 + which) * p.M * 2 : nullptr;
+  }
+  double* red(int b, int which) const { return at<double>(p.red) + ((int64_t)b * 2 + which) * p.M * 2; }
+};
+
+static int check_io(const ctn_config* cfg, int M, int T, const void* ws, int64_t ws_bytes, int training) {
+  CTN_TRY(validate(cfg));
+  CTN_REQUIRE(M >= 1 && M <= 65535, "batch size M must be in [1, 65535] (got %d)", M);
+  CTN_REQUIRE(T >= cfg->L, "input has %d samples, fewer than one frame (L=%d)", T, cfg->L);
+  const int64_t need = ctn_workspace_bytes(cfg, M, T, training);
+  CTN_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: need %lld bytes, got %lld", (long long)need,
+              (long long)ws_bytes);
+  CTN_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+static int model_forward(const Ctx& X, const float* mixture, float* est) {
+  const ctn_config& c = X.c;
+  const Plan& p = X.p;
+  const ParamLayout& L = X.L;
+  const int M = p.M, K = p.K, nblk = p.nblk;
+  const int64_t F = p.F;
+  cudaStream_t s = X.s;
+  const bool gln = c.norm_type == CTN_NORM_GLN;
+
+  if (gln) CTN_CUDA(cudaMemsetAsync(X.at<char>(p.gacc), 0, (size_t)nblk * 2 * M * 2 * 8, s));
+  // norm-fold constants for the bottleneck and every block's pointwise conv (one launch each)
+  CTN_TRY(run_prep_normfold(X.params + L.Wb, X.params + L.g0, X.params + L.b0, c.B, c.N, 1, 0, X.at<float>(p.Wbg),
+                            X.at<float>(p.c1b), X.at<float>(p.c2b), 0, 0, s));
+  CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
+                            X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
+  // encoder + first cLN statistics + bottleneck (cLN folded into the GEMM epilogue)
+  float* w = X.at<float>(p.w);
+  CTN_TRY(run_encoder_fwd(mixture, X.params + L.U, M, p.T, c.N, c.L, w, s));
+  CTN_TRY(run_row_stats(w, nullptr, F, c.N, X.at<float>(p.rowstat0), s));
+  {
+    GemmArgs a = {};
+    a.A = w; a.W = X.at<float>(p.Wbg); a.D = X.x(0); a.F = F; a.O = c.B; a.Kd = c.N; a.K = K;
+    a.c1 = X.at<float>(p.c1b); a.c2 = X.at<float>(p.c2b);
+    a.st.row = X.at<float>(p.rowstat0);
+    CTN_TRY(launch_gemm(a, s));
+  }
+  for (int b = 0; b < nblk; ++b) {
+    const int dil = 1 << (b % c.X);
+    {  // z1 = x W1^T, gLN stats of prelu(z1)
+      GemmArgs a = {};
+      a.A = X.x(b); a.W = X.blk(b, L.W1); a.D = X.z1(b); a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
+      a.stat_out = X.stat_out(b, 0); a.alpha_out = X.blk(b, L.a1);
+      CTN_TRY(launch_gemm(a, s));
+    }
+    if (!gln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
+    CTN_TRY(run_dwconv_fwd(X.z1(b), X.blk(b, L.a1), X.stats(b, 0), X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K,
+                           c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s));
+    if (!gln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s));
+    {  // out = x + norm2(prelu(z2)) W2^T with norm2 folded
+      GemmArgs a = {};
+      a.A = X.z2(b); a.W = X.at<float>(p.W2g) + (int64_t)b * c.B * c.H; a.D = X.x(b + 1);
+      a.F = F; a.O = c.B; a.Kd = c.H; a.K = K;
+      a.alpha_in = X.blk(b, L.a2);
+      a.c1 = X.at<float>(p.c1) + (int64_t)b * c.B; a.c2 = X.at<float>(p.c2) + (int64_t)b * c.B;
+      a.st = X.stats(b, 1);
+      a.res = X.x(b);
+      CTN_TRY(launch_gemm(a, s));
+    }
+  }
+  {  // mask conv
+    GemmArgs a = {};
+    a.A = X.x(nblk); a.W = X.params + L.Wm; a.D = X.at<float>(p.score); a.F = F; a.O = c.C * c.N; a.Kd = c.B; a.K = K;
+    CTN_TRY(launch_gemm(a, s));
+  }
+  return run_decoder_fwd(X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
+                         c.mask_nonlinear == CTN_MASK_SOFTMAX, est, s);
+}
+
+// stages: 0 = zero-init + decoder + mask conv; 1..R = repeat R-stage (its X blocks, last first); R+1 = bottleneck,
+// first cLN, encoder.  Each stage completes one contiguous slice of the flat gradient (ctn_grad_bucket).
+static int model_backward(const Ctx& X, const float* mixture, const float* d_est, float* grads, int accumulate,
+                          int stage_lo, int stage_hi) {
+  const ctn_config& c = X.c;
+  const Plan& p = X.p;
+  const ParamLayout& L = X.L;
+  const int M = p.M, K = p.K, nblk = p.nblk;
+  const int64_t F = p.F;
+  cudaStream_t s = X.s;
+  const bool gln = c.norm_type == CTN_NORM_GLN;
+  auto gblk = [&](int b, int64_t off) { return grads + L.blk0 + (int64_t)b * L.blk_stride + off; };
+
+  float* w = X.at<float>(p.w);
+  float* g_buf[2] = {X.at<float>(p.g), X.at<float>(p.g + al256(F * c.B * 4))};
+  float* dn2 = X.at<float>(p.dn2);
+  float* dn1 = X.at<float>(p.dn1);
+  float* d_score = X.at<float>(p.d_score);
+  float* d_w = X.at<float>(p.d_w);
+  float* dn0 = X.at<float>(p.dn0);
+
+  if (stage_lo <= 0 && 0 < stage_hi) {
+  float* g_cur = g_buf[0];
+  if (!accumulate) CTN_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * 4, s));
+  CTN_CUDA(cudaMemsetAsync(X.at<char>(p.red), 0, (size_t)(nblk * 2 + 1) * M * 2 * 8, s));
+  CTN_TRY(run_decoder_bwd(d_est, X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
+                          c.mask_nonlinear == CTN_MASK_SOFTMAX, d_score, d_w, grads + L.V, s));
+  {  // mask conv: dWm, g = d_score Wm
+    WgradArgs wa = {};
+    wa.G = d_score; wa.Act = X.x(nblk); wa.dW = grads + L.Wm; wa.F = F; wa.O = c.C * c.N; wa.I = c.B; wa.K = K;
+    CTN_TRY(launch_wgrad(wa, s));
+    GemmArgs a = {};
+    a.A = d_score; a.W = X.params + L.Wm; a.w_is_kn = 1; a.D = g_cur; a.F = F; a.O = c.B; a.Kd = c.C * c.N; a.K = K;
+    CTN_TRY(launch_gemm(a, s));
+  }
+  }
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int stage = c.R - b / c.X;
+    if (stage < stage_lo || stage >= stage_hi) continue;
+    const int swaps = nblk - 1 - b;  // ping-pong state is a function of the block index => stages are restartable
+    float* g_cur = g_buf[swaps & 1];
+    float* g_nxt = g_buf[(swaps + 1) & 1];
+    const int dil = 1 << (b % c.X);
+    const NormStats st1 = X.stats(b, 0), st2 = X.stats(b, 1);
+    {  // dn2 = g W2
+      GemmArgs a = {};
+      a.A = g_cur; a.W = X.blk(b, L.W2); a.w_is_kn = 1; a.D = dn2; a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
+      CTN_TRY(launch_gemm(a, s));
+    }
+    {  // dW2 = g^T norm2(prelu(z2))
+      WgradArgs wa = {};
+      wa.G = g_cur; wa.Act = X.z2(b); wa.dW = gblk(b, L.W2); wa.F = F; wa.O = c.B; wa.I = c.H; wa.K = K;
+      wa.alpha = X.blk(b, L.a2); wa.gamma = X.blk(b, L.g2); wa.beta = X.blk(b, L.b2); wa.st = st2;
+      CTN_TRY(launch_wgrad(wa, s));
+    }
+    CTN_TRY(run_norm_bwd_reduce(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), M, K, c.H, gblk(b, L.g2),
+                                gblk(b, L.b2), gln ? X.red(b, 1) : nullptr, s));
+    CTN_TRY(run_norm_bwd_apply(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), M, K, c.H,
+                               gblk(b, L.a2), s));
+    CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K, c.H,
+                           c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1),
+                           gln ? X.red(b, 0) : nullptr, s));
+    CTN_TRY(run_norm_bwd_apply(dn1, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.red(b, 0), M, K, c.H,
+                               gblk(b, L.a1), s));
+    {  // dW1 = dz1^T x
+      WgradArgs wa = {};
+      wa.G = dn1; wa.Act = X.x(b); wa.dW = gblk(b, L.W1); wa.F = F; wa.O = c.H; wa.I = c.B; wa.K = K;
+      CTN_TRY(launch_wgrad(wa, s));
+    }
+    {  // g_prev = g + dz1 W1
+      GemmArgs a = {};
+      a.A = dn1; a.W = X.blk(b, L.W1); a.w_is_kn = 1; a.D = g_nxt; a.F = F; a.O = c.B; a.Kd = c.H; a.K = K;
+      a.res = g_cur;
+      CTN_TRY(launch_gemm(a, s));
+    }
+  }
+  if (!(stage_lo <= c.R + 1 && c.R + 1 < stage_hi)) return 0;
+  // bottleneck + first cLN + encoder
+  float* g_cur = g_buf[nblk & 1];
+  NormStats st0 = {};
+  st0.row = X.at<float>(p.rowstat0);
+  {
+    WgradArgs wa = {};
+    wa.G = g_cur; wa.Act = w; wa.dW = grads + L.Wb; wa.F = F; wa.O = c.B; wa.I = c.N; wa.K = K;
+    wa.gamma = X.params + L.g0; wa.beta = X.params + L.b0; wa.st = st0;
+    CTN_TRY(launch_wgrad(wa, s));
+    GemmArgs a = {};
+    a.A = g_cur; a.W = X.params + L.Wb; a.w_is_kn = 1; a.D = dn0; a.F = F; a.O = c.N; a.Kd = c.B; a.K = K;
+    CTN_TRY(launch_gemm(a, s));
+  }
+  CTN_TRY(run_norm_bwd_reduce(dn0, w, nullptr, st0, X.params + L.g0, M, K, c.N, grads + L.g0, grads + L.b0, nullptr, s));
+  CTN_TRY(run_norm_bwd_apply(dn0, w, nullptr, st0, X.params + L.g0, nullptr, M, K, c.N, nullptr, s));
+  return run_encoder_bwd(mixture, w, dn0, d_w, M, p.T, c.N, c.L, grads + L.U, s);
+}
+
+}  // namespace ctn
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ctn;
+
+extern "C" {
+
+int32_t ctn_version(void) { return 100; }
+int64_t ctn_launch_count(void) { return (int64_t)__atomic_load_n(&ctn::g_launches, __ATOMIC_RELAXED); }
+const char* ctn_last_error(void) { return ctn::last_error(); }
+
+int32_t ctn_param_tensors(const ctn_config* cfg) { return cfg ? 4 + 9 * cfg->R * cfg->X + 2 : 0; }
+
+int64_t ctn_param_floats(const ctn_config* cfg) {
+  if (validate(cfg)) return -1;
+  return make_layout(*cfg).total;
+}
+
+int32_t ctn_param_layout(const ctn_config* cfg, int64_t* offsets, int64_t* numels, int32_t n) {
+  CTN_TRY(validate(cfg));
+  CTN_REQUIRE(n == ctn_param_tensors(cfg), "param_layout: expected %d entries, got %d", ctn_param_tensors(cfg), n);
+  const ctn_config& c = *cfg;
+  const ParamLayout L = make_layout(c);
+  int i = 0;
+  auto put = [&](int64_t off, int64_t ne) { offsets[i] = off; numels[i] = ne; ++i; };
+  put(L.U, (int64_t)c.N * c.L);
+  put(L.g0, c.N);
+  put(L.b0, c.N);
+  put(L.Wb, (int64_t)c.B * c.N);
+  for (int b = 0; b < c.R * c.X; ++b) {
+    const int64_t o = L.blk0 + (int64_t)b * L.blk_stride;
+    put(o + L.W1, (int64_t)c.H * c.B);
+    put(o + L.a1, 1);
+    put(o + L.g1, c.H);
+    put(o + L.b1, c.H);
+    put(o + L.Wd, (int64_t)c.H * c.P);
+    put(o + L.a2, 1);
+    put(o + L.g2, c.H);
+    put(o + L.b2, c.H);
+    put(o + L.W2, (int64_t)c.B * c.H);
+  }
+  put(L.Wm, (int64_t)c.C * c.N * c.B);
+  put(L.V, (int64_t)c.L * c.N);
+  return 0;
+}
+
+int32_t ctn_num_frames(const ctn_config* cfg, int32_t T) {
+  if (!cfg || cfg->L < 2 || T < cfg->L) return 0;
+  return (T - cfg->L) / (cfg->L / 2) + 1;
+}
+
+int64_t ctn_workspace_bytes(const ctn_config* cfg, int32_t M, int32_t T, int32_t training) {
+  if (validate(cfg) || M < 1 || T < cfg->L) return -1;
+  return make_plan(*cfg, M, T, training).total;
+}
+
+int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const float* mixture, int32_t M, int32_t T,
+                          float* est, void* workspace, int64_t workspace_bytes, int32_t training, cudaStream_t stream) {
+  CTN_TRY(check_io(cfg, M, T, workspace, workspace_bytes, training));
+  CTN_REQUIRE(params && mixture && est, "model_forward: null pointer");
+  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, training), params, reinterpret_cast<char*>(workspace), stream};
+  return model_forward(X, mixture, est);
+}
+
+int32_t ctn_model_backward(const ctn_config* cfg, const float* params, const float* mixture, int32_t M, int32_t T,
+                           const float* d_est, float* grads, void* workspace, int64_t workspace_bytes,
+                           int32_t accumulate, cudaStream_t stream) {
+  CTN_TRY(check_io(cfg, M, T, workspace, workspace_bytes, 1));
+  CTN_REQUIRE(params && mixture && d_est && grads, "model_backward: null pointer");
+  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, 1), params, reinterpret_cast<char*>(workspace), stream};
+  return model_backward(X, mixture, d_est, grads, accumulate, 0, cfg->R + 2);
+}
+
+int32_t ctn_model_backward_stage(const ctn_config* cfg, const float* params, const float* mixture, int32_t M, int32_t T,
+                                 const float* d_est, float* grads, void* workspace, int64_t workspace_bytes,
+                                 int32_t accumulate, int32_t stage, cudaStream_t stream) {
+  CTN_TRY(check_io(cfg, M, T, workspace, workspace_bytes, 1));
+  CTN_REQUIRE(params && mixture && d_est && grads, "model_backward_stage: null pointer");
+  CTN_REQUIRE(stage >= 0 && stage < cfg->R + 2, "model_backward_stage: stage %d out of [0,%d)", stage, cfg->R + 2);
+  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, 1), params, reinterpret_cast<char*>(workspace), stream};
+  return model_backward(X, mixture, d_est, grads, accumulate, stage, stage + 1);
+}
+
+int32_t ctn_grad_bucket(const ctn_config* cfg, int32_t stage, int64_t* offset, int64_t* count) {
+  CTN_TRY(validate(cfg));
+  CTN_REQUIRE(stage >= 0 && stage < cfg->R + 2 && offset && count, "grad_bucket: bad arguments");
+  const ParamLayout L = make_layout(*cfg);
+  if (stage == 0) {
+    *offset = L.Wm; *count = L.total - L.Wm;
+  } else if (stage <= cfg->R) {
+    const int r = cfg->R - stage;
+    *offset = L.blk0 + (int64_t)r * cfg->X * L.blk_stride; *count = (int64_t)cfg->X * L.blk_stride;
+  } else {
+    *offset = 0; *count = L.blk0;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""The step tail of src/solver.py:192-196 — clip_grad_norm_(max_norm) + Adam — fused on the model's flat parameter /
+gradient buffers (ctn_clip_grad_norm, ctn_adam_step): 4 kernel launches instead of ~30 multi-tensor ones over 294
+tensors, and no host sync (the norm stays on the device unless asked for)."""
+import torch
+
+from . import _lib
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics on ConvTasNet.flat_params / flat_grads."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        p = model.flat_params
+        if not p.is_cuda:
+            raise RuntimeError("FusedAdam runs on CUDA only (no CPU fallback); move the model to the GPU first")
+        self.exp_avg = torch.zeros_like(p)
+        self.exp_avg_sq = torch.zeros_like(p)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=p.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=p.device)
+        self._scratch = torch.empty(8192, dtype=torch.uint8, device=p.device)
+
+    def zero_grad(self, set_to_none=False):
+        # the backward overwrites the flat gradient buffer; only detach per-parameter views if asked to
+        if set_to_none:
+            for p in self.model.parameters():
+                p.grad = None
+
+    def step(self):
+        m = self.model
+        p, g = m.flat_params, m.flat_grads
+        if p.data_ptr() != self.exp_avg.data_ptr() and p.numel() != self.exp_avg.numel():
+            raise RuntimeError("model was re-flattened with a different size after FusedAdam was built")
+        L = _lib.lib()
+        with torch.cuda.device(p.device):
+            if self.max_grad_norm is not None:
+                _lib.check(L.ctn_clip_grad_norm(_lib.ptr(g), g.numel(), float(self.max_grad_norm),
+                                                _lib.ptr(self.grad_norm), _lib.ptr(self._scratch), _lib.stream()))
+            _lib.check(L.ctn_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                       p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                       _lib.ptr(self.step_count), _lib.stream()))
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps,
+                                  "weight_decay": self.weight_decay}]}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count.copy_(sd["step"])
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]

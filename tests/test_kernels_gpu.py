@@ -1,0 +1,293 @@
+"""Parity of every CUDA kernel (called through the C ABI) with the kernel-level oracle oracle/fused_schedule.py,
+on seeded inputs, at sizes the oracle finishes in seconds.  Tolerances are max|a-b|/max|b| (conftest.rel_err):
+fp32 forward ops 1e-5 (north-star budget is 1e-4 end to end), reductions/gradients 1e-4 (budget 1e-3)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from gpu_util import P, call, dev, gln_acc, stats_args
+from oracle import conv_tasnet_oracle as O
+from oracle import fused_schedule as FS
+
+pytestmark = pytest.mark.gpu
+TOL_F, TOL_G = 1e-5, 1e-4
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev())
+
+
+def cfg_of(**kw):
+    base = dict(N=16, L=8, B=8, H=16, P=3, X=2, R=1, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu")
+    base.update(kw)
+    return O.Config(**base)
+
+
+@pytest.mark.parametrize("M,T,N,L", [(2, 403, 16, 8), (3, 32000, 256, 20), (1, 131, 8, 4), (2, 100, 12, 5)])
+def test_encoder_fwd_bwd(M, T, N, L):
+    mix, U = rnd(M, T, seed=1, scale=0.1), rnd(N, L, seed=2, scale=0.3)
+    K = O.n_frames(T, L)
+    w = torch.empty(M, K, N, device=dev())
+    call("ctn_encoder_fwd", P(mix), P(U), M, T, N, L, P(w))
+    want = FS.encoder_fwd(mix.cpu(), U.cpu())
+    assert rel_err(w.cpu(), want) < TOL_F
+    dwa, dwb = rnd(M, K, N, seed=3), rnd(M, K, N, seed=4)
+    dU = torch.zeros(N, L, device=dev())
+    call("ctn_encoder_bwd", P(mix), P(w), P(dwa), P(dwb), M, T, N, L, P(dU))
+    want = FS.encoder_bwd(mix.cpu().double(), want.double(), (dwa + dwb).cpu().double(), L)
+    assert rel_err(dU.cpu(), want) < TOL_G
+
+
+@pytest.mark.parametrize("F,Ch,prelu", [(403, 16, False), (9597, 512, True), (77, 20, True)])
+def test_row_stats(F, Ch, prelu):
+    x = rnd(1, F, Ch, seed=5) + 0.3
+    alpha = torch.tensor([0.17], device=dev()) if prelu else None
+    out = torch.empty(F, 2, device=dev())
+    call("ctn_row_stats", P(x), P(alpha), F, Ch, P(out))
+    a = FS.prelu(x.cpu().double(), 0.17) if prelu else x.cpu().double()
+    mu, r = FS.row_stats(a)
+    assert rel_err(out[:, 0].cpu(), mu.view(-1)) < TOL_F
+    assert rel_err(out[:, 1].cpu(), r.view(-1)) < TOL_F
+
+
+@pytest.mark.parametrize("M,K,Kd,Ochan", [(2, 99, 8, 16), (3, 3199, 256, 512), (3, 3199, 512, 256), (1, 130, 36, 8),
+                                            (2, 257, 20, 12)])
+@pytest.mark.parametrize("kn", [0, 1])
+def test_conv1x1_plain_and_stats(M, K, Kd, Ochan, kn):
+    A, W = rnd(M, K, Kd, seed=6), rnd(Ochan, Kd, seed=7, scale=1 / math.sqrt(Kd))
+    Wdev = W.t().contiguous() if kn else W
+    D = torch.empty(M, K, Ochan, device=dev())
+    alpha_out = torch.tensor([0.21], device=dev())
+    stat = torch.zeros(M, 2, dtype=torch.float64, device=dev())
+    call("ctn_conv1x1", P(A), P(Wdev), kn, P(D), M * K, Ochan, Kd, K, None, None, None, None, None, None, P(stat),
+         P(alpha_out))
+    want = A.cpu().double() @ W.cpu().double().t()
+    assert rel_err(D.cpu(), want) < TOL_F
+    assert rel_err(stat.cpu(), gln_acc(FS.prelu(want, 0.21))) < TOL_F
+
+
+@pytest.mark.parametrize("norm", ["gLN", "cLN"])
+@pytest.mark.parametrize("M,K,Kd,Ochan", [(2, 99, 16, 8), (3, 3199, 512, 256), (5, 37, 20, 12)])
+def test_conv1x1_prelu_normfold_residual(norm, M, K, Kd, Ochan):
+    z, W = rnd(M, K, Kd, seed=8) + 0.2, rnd(Ochan, Kd, seed=9, scale=1 / math.sqrt(Kd))
+    gamma, beta, res = rnd(Kd, seed=10), rnd(Kd, seed=11), rnd(M, K, Ochan, seed=12)
+    alpha = torch.tensor([0.3], device=dev())
+    a = FS.prelu(z.cpu().double(), 0.3)
+    acc, rs, (mu, r) = stats_args(norm, a)
+    acc, rs = (None if acc is None else acc.to(dev())), (None if rs is None else rs.to(dev()))
+    Wg, c1, c2 = torch.empty_like(W), torch.empty(Ochan, device=dev()), torch.empty(Ochan, device=dev())
+    call("ctn_prep_normfold", P(W), P(gamma), P(beta), Ochan, Kd, P(Wg), P(c1), P(c2))
+    assert rel_err(Wg.cpu(), (W * gamma.view(1, -1)).cpu()) < 1e-6
+    assert rel_err(c1.cpu(), (W.cpu().double() @ beta.cpu().double())) < TOL_F
+    D = torch.empty(M, K, Ochan, device=dev())
+    call("ctn_conv1x1", P(z), P(Wg), 0, P(D), M * K, Ochan, Kd, K, P(alpha), P(c1), P(c2), P(acc), P(rs), P(res), None,
+         None)
+    mu_d, r_d = (FS.sample_stats(a) if norm == "gLN" else FS.row_stats(a))
+    want = FS.gemm_normfold(a, mu_d, r_d, W.cpu().double(), gamma.cpu().double(), beta.cpu().double(),
+                            res.cpu().double())
+    assert rel_err(D.cpu(), want) < TOL_F
+
+
+@pytest.mark.parametrize("norm", [None, "gLN", "cLN"])
+@pytest.mark.parametrize("M,K,Ochan,I", [(2, 99, 8, 16), (3, 3199, 256, 512), (3, 3199, 512, 256), (4, 50, 36, 8)])
+def test_wgrad(norm, M, K, Ochan, I):
+    G, z = rnd(M, K, Ochan, seed=13), rnd(M, K, I, seed=14) + 0.1
+    dW = torch.zeros(Ochan, I, device=dev())
+    if norm is None:
+        call("ctn_wgrad", P(G), P(z), P(dW), M * K, Ochan, I, K, None, None, None, None, None)
+        act = z.cpu().double()
+    else:
+        gamma, beta = rnd(I, seed=15), rnd(I, seed=16)
+        alpha = torch.tensor([0.3], device=dev())
+        a = FS.prelu(z.cpu().double(), 0.3)
+        acc, rs, _ = stats_args(norm, a)
+        acc, rs = (None if acc is None else acc.to(dev())), (None if rs is None else rs.to(dev()))
+        call("ctn_wgrad", P(G), P(z), P(dW), M * K, Ochan, I, K, P(alpha), P(gamma), P(beta), P(acc), P(rs))
+        mu, r = FS.sample_stats(a) if norm == "gLN" else FS.row_stats(a)
+        act = gamma.cpu().double().view(1, 1, -1) * (a - mu) * r + beta.cpu().double().view(1, 1, -1)
+    want = torch.einsum("mko,mki->oi", G.cpu().double(), act)
+    assert rel_err(dW.cpu(), want) < TOL_G
+
+
+@pytest.mark.parametrize("norm", ["gLN", "cLN"])
+@pytest.mark.parametrize("causal,Pk,dil", [(False, 3, 1), (False, 3, 16), (True, 3, 4), (True, 2, 2), (False, 5, 2),
+                                           (False, 3, 128)])
+@pytest.mark.parametrize("M,K,H", [(2, 99, 16), (3, 400, 512)])
+def test_dwconv_fwd_bwd(norm, causal, Pk, dil, M, K, H):
+    cfg = cfg_of(causal=causal, P=Pk, H=H, norm_type=norm)
+    z1 = rnd(M, K, H, seed=17) + 0.1
+    g1, b1, Wd = rnd(H, seed=18), rnd(H, seed=19), rnd(H, Pk, seed=20)
+    a1, a2 = torch.tensor([0.25], device=dev()), torch.tensor([0.4], device=dev())
+    a = FS.prelu(z1.cpu().double(), 0.25)
+    acc, rs, _ = stats_args(norm, a)
+    acc, rs = (None if acc is None else acc.to(dev())), (None if rs is None else rs.to(dev()))
+    mu, r = FS.sample_stats(a) if norm == "gLN" else FS.row_stats(a)
+    z2 = torch.empty_like(z1)
+    stat = torch.zeros(M, 2, dtype=torch.float64, device=dev())
+    call("ctn_dwconv_fwd", P(z1), P(a1), P(acc), P(rs), P(g1), P(b1), P(Wd), M, K, H, Pk, dil, int(causal), P(z2),
+         P(stat), P(a2))
+    want = FS.dwconv_fwd(cfg, z1.cpu().double(), 0.25, mu, r, g1.cpu().double(), b1.cpu().double(), Wd.cpu().double(),
+                         dil)
+    assert rel_err(z2.cpu(), want) < TOL_F
+    assert rel_err(stat.cpu(), gln_acc(FS.prelu(want, 0.4))) < TOL_F
+    # backward
+    dz2 = rnd(M, K, H, seed=21)
+    dn1 = torch.empty_like(z1)
+    dWd, dg, db = torch.zeros(H, Pk, device=dev()), torch.zeros(H, device=dev()), torch.zeros(H, device=dev())
+    red = torch.zeros(M, 2, dtype=torch.float64, device=dev())
+    call("ctn_dwconv_bwd", P(dz2), P(z1), P(a1), P(acc), P(rs), P(g1), P(b1), P(Wd), M, K, H, Pk, dil, int(causal),
+         P(dn1), P(dWd), P(dg), P(db), P(red))
+    w_dn1, w_dWd = FS.dwconv_bwd(cfg, dz2.cpu().double(), z1.cpu().double(), 0.25, mu, r, g1.cpu().double(),
+                                 b1.cpu().double(), Wd.cpu().double(), dil)
+    assert rel_err(dn1.cpu(), w_dn1) < TOL_F
+    assert rel_err(dWd.cpu(), w_dWd) < TOL_G
+    yh = (a - mu) * r
+    assert rel_err(dg.cpu(), (w_dn1 * yh).sum(dim=(0, 1))) < TOL_G
+    assert rel_err(db.cpu(), w_dn1.sum(dim=(0, 1))) < TOL_G
+    gh = w_dn1 * g1.cpu().double().view(1, 1, -1)
+    want_red = torch.stack([gh.sum(dim=(1, 2)), (gh * yh).sum(dim=(1, 2))], dim=1)
+    assert rel_err(red.cpu(), want_red) < TOL_G
+
+
+@pytest.mark.parametrize("norm", ["gLN", "cLN"])
+@pytest.mark.parametrize("prelu", [True, False])
+@pytest.mark.parametrize("M,K,Ch", [(2, 99, 16), (3, 700, 512), (1, 33, 20)])
+def test_norm_bwd(norm, prelu, M, K, Ch):
+    cfg = cfg_of(norm_type=norm)
+    z, dn, gamma = rnd(M, K, Ch, seed=22) + 0.1, rnd(M, K, Ch, seed=23), rnd(Ch, seed=24)
+    alpha = torch.tensor([0.35], device=dev()) if prelu else None
+    a = FS.prelu(z.cpu().double(), 0.35) if prelu else z.cpu().double()
+    acc, rs, _ = stats_args(norm, a)
+    acc, rs = (None if acc is None else acc.to(dev())), (None if rs is None else rs.to(dev()))
+    mu, r = FS.sample_stats(a) if norm == "gLN" else FS.row_stats(a)
+    dg, db = torch.zeros(Ch, device=dev()), torch.zeros(Ch, device=dev())
+    red = torch.zeros(M, 2, dtype=torch.float64, device=dev())
+    dalpha = torch.zeros(1, device=dev())
+    call("ctn_norm_bwd_reduce", P(dn), P(z), P(alpha), P(acc), P(rs), P(gamma), M, K, Ch, P(dg), P(db), P(red))
+    dz = dn.clone()
+    call("ctn_norm_bwd_apply", P(dz), P(z), P(alpha), P(acc), P(rs), P(gamma), P(red), M, K, Ch,
+         P(dalpha) if prelu else None)
+    w_dz, w_dg, w_db, w_da = FS.norm_bwd(cfg, dn.cpu().double(), z.cpu().double(),
+                                         torch.tensor(0.35, dtype=torch.float64) if prelu else None, mu, r,
+                                         gamma.cpu().double())
+    assert rel_err(dz.cpu(), w_dz) < TOL_G
+    assert rel_err(dg.cpu(), w_dg) < TOL_G
+    assert rel_err(db.cpu(), w_db) < TOL_G
+    if prelu:
+        assert abs(dalpha.item() - w_da.item()) < TOL_G * max(1.0, abs(w_da.item()), w_dz.abs().sum().item() * 1e-3)
+
+
+@pytest.mark.parametrize("softmax", [0, 1])
+@pytest.mark.parametrize("M,K,C,N,L,pad", [(2, 99, 2, 16, 8, 3), (3, 3199, 2, 256, 20, 0), (2, 64, 3, 12, 6, 5),
+                                            (1, 40, 2, 8, 5, 0), (2, 33, 4, 8, 4, 1)])
+def test_decoder_fwd_bwd(softmax, M, K, C, N, L, pad):
+    cfg = cfg_of(C=C, N=N, L=L, mask_nonlinear="softmax" if softmax else "relu")
+    S = L // 2
+    T = (K - 1) * S + L + pad
+    score, w, V = rnd(M, K, C * N, seed=25), rnd(M, K, N, seed=26).abs(), rnd(L, N, seed=27, scale=0.2)
+    est = torch.full((M, C, T), float("nan"), device=dev())
+    call("ctn_decoder_fwd", P(score), P(w), P(V), M, K, C, N, L, T, softmax, P(est))
+    want = FS.decoder_fwd(cfg, score.cpu().double(), w.cpu().double(), V.cpu().double(), T)
+    assert rel_err(est.cpu(), want) < TOL_F
+    d_est = rnd(M, C, T, seed=28)
+    d_score, d_w = torch.empty_like(score), torch.empty_like(w)
+    dV = torch.zeros(L, N, device=dev())
+    call("ctn_decoder_bwd", P(d_est), P(score), P(w), P(V), M, K, C, N, L, T, softmax, P(d_score), P(d_w), P(dV))
+    w_ds, w_dw, w_dV = FS.decoder_bwd(cfg, d_est.cpu().double(), score.cpu().double(), w.cpu().double(),
+                                      V.cpu().double())
+    assert rel_err(d_score.cpu(), w_ds) < TOL_F
+    assert rel_err(d_w.cpu(), w_dw) < TOL_F
+    assert rel_err(dV.cpu(), w_dV) < TOL_G
+
+
+def test_overlap_and_add_golden_bit_exact():
+    from conv_tasnet_b200.utils import overlap_and_add
+    z = load_golden("ola.npz")
+    out = overlap_and_add(torch.from_numpy(z["kat_signal"]).float().to(dev()), int(z["kat_step"]))
+    assert torch.equal(out.cpu(), torch.from_numpy(z["kat_result"]).float())  # reference's own known answer
+    for i in range(int(z["n_random"])):
+        sig, step = torch.from_numpy(z[f"r{i}_signal"]).to(dev()), int(z[f"r{i}_step"])
+        want = torch.from_numpy(z[f"r{i}_result"])
+        got = overlap_and_add(sig, step).cpu()
+        assert got.shape == want.shape
+        if sig.shape[-1] <= 2 * step:
+            assert torch.equal(got, want)  # <= 2 contributors: order independent => bit exact
+        else:
+            assert rel_err(got, want) < 1e-6
+    with pytest.raises(ValueError):
+        overlap_and_add(torch.zeros(1, 3, 4, device=dev()), 5)
+
+
+def test_pit_golden_bit_exact_choice():
+    from conv_tasnet_b200.pit_criterion import cal_loss, cal_si_snr_with_pit, reorder_source
+    z = load_golden("pit.npz")
+    # the reference's seed-123 known answer
+    src = torch.from_numpy(z["kat_source"]).float().to(dev())
+    est = torch.from_numpy(z["kat_est"]).float().to(dev())
+    loss, max_snr, est_m, reord = cal_loss(src, est, torch.from_numpy(z["kat_lengths"]))
+    assert abs(loss.item() - 45.9221) < 2e-4 and abs(loss.item() - float(z["kat_loss"])) < 1e-4
+    assert max_snr.shape == (2, 1) and np.allclose(max_snr.cpu().numpy(), z["kat_max_snr"], atol=1e-4)
+    assert abs(reord.double().sum().item() - float(z["kat_reorder_crc"])) < 1e-6
+    assert est_m.data_ptr() == est.data_ptr()  # masked in place, same object returned
+    for i in range(int(z["n_cases"])):
+        src = torch.from_numpy(z[f"c{i}_source"]).to(dev())
+        est_in = torch.from_numpy(z[f"c{i}_est"]).to(dev()).requires_grad_(True)
+        lens = torch.from_numpy(z[f"c{i}_lengths"])
+        est = est_in * 1.0
+        loss, max_snr, est_m, reord = cal_loss(src, est, lens if i % 2 else lens.to(dev()))
+        loss.backward()
+        assert abs(loss.item() - float(z[f"c{i}_loss"])) < 1e-3
+        assert rel_err(max_snr.cpu(), z[f"c{i}_max_snr"]) < 1e-4
+        assert torch.equal(est_m.detach().cpu(), torch.from_numpy(z[f"c{i}_est_masked"]))
+        assert torch.equal(reord.cpu(), torch.from_numpy(z[f"c{i}_reorder"]))  # bit exact reorder
+        assert rel_err(est_in.grad.cpu(), z[f"c{i}_grad_est"]) < 1e-3
+        ms, perms, idx = cal_si_snr_with_pit(src, torch.from_numpy(z[f"c{i}_est"]).to(dev()), lens)
+        assert torch.equal(perms.cpu(), torch.from_numpy(z[f"c{i}_perms"]))
+        assert torch.equal(idx.cpu(), torch.from_numpy(z[f"c{i}_idx"]))  # bit exact permutation choice
+        r2 = reorder_source(torch.from_numpy(z[f"c{i}_est_masked"]).to(dev()), perms, idx)
+        assert torch.equal(r2.cpu(), torch.from_numpy(z[f"c{i}_reorder"]))
+
+
+def test_pit_full_size_properties():
+    """BASELINE sizes: permuting the estimates permutes the chosen index consistently and leaves the loss unchanged."""
+    from conv_tasnet_b200.pit_criterion import cal_loss
+    g = torch.Generator().manual_seed(3)
+    B, C, T = 16, 3, 32000
+    src = (torch.randn(B, C, T, generator=g) * 0.05).to(dev())
+    est = src[:, [2, 0, 1]] + 0.02 * torch.randn(B, C, T, generator=g).to(dev())
+    lens = torch.full((B,), T)
+    l1, s1, _, r1 = cal_loss(src, est.clone(), lens)
+    l2, s2, _, r2 = cal_loss(src, est[:, [1, 2, 0]].clone(), lens)
+    assert abs(l1.item() - l2.item()) < 1e-4
+    ref = O.cal_loss(src.cpu(), est.cpu().clone(), lens)
+    assert abs(l1.item() - ref[0].item()) < 1e-3
+    assert torch.equal(r1.cpu(), ref[3])
+
+
+def test_clip_and_adam_match_torch():
+    n = 100003
+    g = torch.Generator().manual_seed(9)
+    p0, g0 = torch.randn(n, generator=g), torch.randn(n, generator=g) * 0.1
+    pt = torch.nn.Parameter(p0.clone().to(dev()))
+    opt = torch.optim.Adam([pt], lr=1e-3)
+    p = p0.clone().to(dev())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device=dev())
+    scratch = torch.empty(8192, dtype=torch.uint8, device=dev())
+    norm = torch.empty(1, device=dev())
+    for it in range(3):
+        gi = (g0 * (it + 1) * 30).to(dev())
+        pt.grad = gi.clone()
+        tn = torch.nn.utils.clip_grad_norm_([pt], 5.0)
+        opt.step()
+        gc = gi.clone()
+        call("ctn_clip_grad_norm", P(gc), n, 5.0, P(norm), P(scratch))
+        assert abs(norm.item() - tn.item()) < 1e-4 * tn.item()
+        assert rel_err(gc.cpu(), pt.grad.cpu()) < 1e-6
+        call("ctn_adam_step", P(p), P(gc), P(m), P(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, P(step))
+        assert rel_err(p.cpu(), pt.detach().cpu()) < 1e-6
+    assert step.item() == 3
