@@ -130,6 +130,7 @@ class ConvTasNet(nn.Module):
         self._layout = None
         self._ws_cache = {}
         self._grad_sync = None  # set by data_parallel.ShardedDataParallel
+        self._overwrite_next = False  # set by optim.FusedAdam: the next backward overwrites the flat gradients
         self._plist = None
 
     # ------------------------------------------------------------------ flat parameter storage
@@ -253,9 +254,10 @@ class ConvTasNet(nn.Module):
             accumulate, target = 0, grads
         elif n_none == 0 and plist[0].grad.data_ptr() == grads.data_ptr() + 4 * self._layout[0][0] \
                 and plist[-1].grad.data_ptr() == grads.data_ptr() + 4 * self._layout[0][-1]:
-            accumulate, target = 1, grads
+            accumulate, target = (0 if self._overwrite_next else 1), grads
         else:  # mixed ownership of .grad: compute aside and add per tensor (slow path)
             accumulate, target = 0, torch.empty_like(grads)
+        self._overwrite_next = False
         args = (ctypes.byref(self._cfg), _lib.ptr(self._flat), _lib.ptr(mixture), M, T, _lib.ptr(d_est),
                 _lib.ptr(target), _lib.ptr(ws), ws.numel(), accumulate)
         with torch.cuda.device(mixture.device):

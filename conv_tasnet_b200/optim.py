@@ -23,7 +23,8 @@ class FusedAdam:
         self._scratch = torch.empty(8192, dtype=torch.uint8, device=p.device)
 
     def zero_grad(self, set_to_none=False):
-        # the backward overwrites the flat gradient buffer; only detach per-parameter views if asked to
+        # the next backward overwrites the flat gradient buffer (no memset pass over 35 MB, no 294 tiny kernels)
+        self.model._overwrite_next = True
         if set_to_none:
             for p in self.model.parameters():
                 p.grad = None
@@ -41,6 +42,7 @@ class FusedAdam:
             _lib.check(L.ctn_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                        p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                        _lib.ptr(self.step_count), _lib.stream()))
+        m._overwrite_next = True
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,

@@ -1,0 +1,56 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: bucketed gradient all-reduce over the staged
+backward's flat slices, parameter broadcast, batch sharding.  The CUDA kernels are not involved (no GPU here)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, overlap):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conv_tasnet_b200 import ConvTasNet
+    from conv_tasnet_b200.data_parallel import ShardedDataParallel, shard_batch
+    torch.manual_seed(100 + rank)  # different initial weights per rank on purpose
+    model = ConvTasNet(16, 8, 8, 16, 3, 3, 2, 2)
+    dp = ShardedDataParallel(model, overlap=overlap)
+    assert dp.module is model and list(dp.parameters())[0] is list(model.parameters())[0]
+    # broadcast made the replicas identical to rank 0
+    ref = [torch.empty_like(model.flat_params) for _ in range(world)]
+    dist.all_gather(ref, model.flat_params)
+    assert torch.equal(ref[0], ref[1])
+    # staged all-reduce averages every slice of the flat gradient exactly once
+    g = model.flat_grads
+    g.copy_(torch.arange(g.numel(), dtype=torch.float32) * (rank + 1))
+    for stage in range(model.R + 2):
+        model._grad_sync(model, stage)
+    model._grad_sync(model, -1)
+    want = torch.arange(g.numel(), dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    assert torch.allclose(g, want, rtol=1e-6), (g - want).abs().max()
+    assert dp._pending == []
+    # shard_batch = the scatter DataParallel did
+    x = torch.arange(6).view(6, 1)
+    (mine,) = shard_batch(rank, world, x)
+    assert mine.flatten().tolist() == [3 * rank, 3 * rank + 1, 3 * rank + 2]
+    # grad_views alias the flat buffer in parameters() order
+    views = model.grad_views()
+    assert sum(v.numel() for v in views) == sum(p.numel() for p in model.parameters())
+    assert views[0].data_ptr() == g.data_ptr()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_bucketed_allreduce_world2_gloo(overlap):
+    mp.spawn(_worker, args=(2, _free_port(), overlap), nprocs=2, join=True)

@@ -82,14 +82,45 @@ def test_paper_config_seeded_init_forward_loss_grads():
         assert abs(p.grad.double().norm().item() - gn) < 1e-3 * gn + 1e-12, k
 
 
+def test_paper_config2_training_step_against_fp64_truth():
+    """BASELINE configs[1] at full size (paper config, M=3 x 4 s): output, loss and every gradient against fp64 truth
+    (tests/golden/paper_cfg2_fp64.npz).  The reference's own fp32 autograd is up to 2.6e-3 off that truth on PReLU-slope
+    gradients, so fp64 is the only meaningful yardstick for the 1e-3 gradient tolerance."""
+    from conv_tasnet_b200 import ConvTasNet, cal_loss
+    z = load_golden("paper_cfg2_fp64.npz")
+    cfg = O.PAPER
+    sd = O.init_state_dict(cfg, seed=int(z["seed_w"]))
+    model = ConvTasNet(**cfg.as_dict())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    mix, src, lens = O.synthetic_batch(int(z["M"]), int(z["T"]), cfg.C, cfg.L, int(z["seed_x"]))
+    est = model(mix.cuda())
+    loss, max_snr, est_m, _ = cal_loss(src.cuda(), est, lens)
+    loss.backward()
+    sub = est_m.detach().cpu()[..., ::int(z["est_stride"])].double()
+    assert (sub - torch.from_numpy(z["est_sub"]).double()).abs().max().item() / float(z["est_abs_max"]) < 1e-4
+    assert abs(loss.item() - float(z["loss"])) < 0.01
+    assert rel_err(max_snr.cpu(), z["max_snr"]) < 1e-4
+    names = [str(s) for s in z["names"]]
+    assert names == [k for k, _ in model.named_parameters()]
+    worst = (0.0, None)
+    for i, (k, p) in enumerate(model.named_parameters()):
+        f = p.grad.flatten().cpu().double()
+        idx = torch.linspace(0, f.numel() - 1, z["g_samples"].shape[1]).long()
+        e = (f[idx] - torch.from_numpy(z["g_samples"][i])).abs().max().item() / float(z["g_absmax"][i])
+        n = abs(f.norm().item() - float(z["g_norm"][i])) / float(z["g_norm"][i])
+        worst = max(worst, (e, k), (n, k + " (norm)"))
+    assert worst[0] < 1e-3, worst
+
+
 @pytest.mark.parametrize("cfgd,M,T", [
-    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu"), 3, 32000),
-    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=3, norm_type="gLN", causal=False, mask_nonlinear="relu"), 2, 16000),
-    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="cLN", causal=True, mask_nonlinear="relu"), 2, 16000),
+    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=3, norm_type="gLN", causal=False, mask_nonlinear="relu"), 2, 12000),
+    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="cLN", causal=True, mask_nonlinear="relu"), 2, 12000),
+    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="softmax"), 1, 8000),
 ])
-def test_paper_size_against_cpu_oracle(cfgd, M, T):
-    """Full-width models against the CPU oracle on identical seeded inputs and weights (BASELINE configs 2,4,3 at a
-    batch the oracle finishes in seconds)."""
+def test_paper_width_against_fp64_oracle(cfgd, M, T):
+    """Full-width variants (C=3 six-permutation PIT, causal cLN, softmax mask) against the CPU oracle run in fp64 on
+    identical seeded inputs and weights, at a size the oracle finishes in seconds."""
     from conv_tasnet_b200 import ConvTasNet, cal_loss
     cfg = O.Config(**cfgd)
     sd = O.init_state_dict(cfg, seed=0)
@@ -97,16 +128,16 @@ def test_paper_size_against_cpu_oracle(cfgd, M, T):
     model.load_state_dict(sd)
     model = model.cuda().train()
     mix, src, lens = O.synthetic_batch(M, T, cfg.C, cfg.L, 1234)
-    torch.set_num_threads(max(1, torch.get_num_threads()))
-    loss_o, est_o, grads_o, max_snr_o, reord_o = O.train_step_grads(cfg, sd, mix, src, lens)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    loss_o, est_o, grads_o, max_snr_o, reord_o = O.train_step_grads(cfg, sd64, mix.double(), src.double(), lens)
     est = model(mix.cuda())
     loss, max_snr, est_m, reord = cal_loss(src.cuda(), est, lens)
     loss.backward()
     assert rel_err(est_m.detach().cpu(), est_o) < 1e-4
     assert abs(loss.item() - loss_o.item()) < 0.01
     assert rel_err(reord.cpu(), reord_o) < 1e-4
-    worst = max(rel_err(p.grad.cpu(), grads_o[k]) for k, p in model.named_parameters())
-    assert worst < 1e-3, worst
+    worst = max((rel_err(p.grad.cpu(), grads_o[k]), k) for k, p in model.named_parameters())
+    assert worst[0] < 1e-3, worst
 
 
 def test_full_size_properties_causal_cln_batch32():
