@@ -118,6 +118,10 @@ class ConvTasNet(nn.Module):
         self.causal = causal
         self.mask_nonlinear = mask_nonlinear
         self._cfg = _lib.make_config(N, L, B, H, P, X, R, C, norm_type, causal, mask_nonlinear)
+        if self._cfg.mask_nonlinear < 0:
+            # the reference only objects at forward time (src/conv_tasnet.py:213-214): keep a valid geometry config and
+            # let _run_forward raise the ValueError
+            self._cfg.mask_nonlinear = 0
         self.encoder = Encoder(L, N)
         self.separator = TemporalConvNet(N, B, H, P, X, R, C, causal)
         self.decoder = Decoder(N, L)

@@ -47,3 +47,15 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 — the per-tensor gradient metric (see tests/golden/make_golden_fp64.py for why not max-norm)."""
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def grad_tolerance(ref32_err):
+    """1e-3 (north star), or 3x the fp32 reference's own error against fp64 truth where that is larger."""
+    return max(1e-3, 3.0 * ref32_err)

@@ -1,11 +1,16 @@
 """fp64 truth for the full-size training step (BASELINE configs[1]: paper config, M=3 x 4 s), from the oracle.
 
-    python tests/golden/make_golden_fp64.py        (~1 min on 8 cores; needs no reference checkout)
+    python tests/golden/make_golden_fp64.py        (~2 min on 8 cores; needs no reference checkout)
 
-Why fp64: the reference's own fp32 autograd is up to 2.6e-3 away from fp64 on the PReLU-slope gradients of this config
-(4.9 M-term sums), i.e. noisier than the 1e-3 gradient tolerance, so the tolerance is applied against fp64 truth.  The
-fp32 oracle is pinned to the reference by tests/test_oracle_golden.py; this file is the same code in double precision.
-Stored: per-parameter gradient norm + 64 evenly spaced entries, sub-sampled output, loss."""
+Why fp64, and why relative L2: any two fp32 forwards that differ in their last bits flip the sign of a handful of
+pre-activations sitting within rounding distance of a PReLU kink (about 10 per layer here).  Each flip changes one
+term of an n-term random-sign sum in the weight gradients by O(1), i.e. the sum by O(1/sqrt(n)) — 6e-3 for n = 24k
+frames.  The reference's own fp32 autograd is therefore up to 2.6e-3 (max-norm) away from its fp64 self on this config,
+above the 1e-3 gradient tolerance.  The tolerance is applied per tensor in relative L2 against fp64 truth, and the
+fp32 oracle's own error against the same truth is stored next to it as the calibration.
+The fp32 oracle is pinned to the reference by tests/test_oracle_golden.py; this is the same code in double precision.
+Stored per parameter: ||g||2, the entries at `sample_index(numel)` (all of them for tensors <= 4096 elements), and the
+fp32 oracle's relative-L2 error on those entries; plus the sub-sampled output and the loss."""
 import os
 import sys
 
@@ -16,24 +21,36 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import conv_tasnet_oracle as O  # noqa: E402
 
-torch.set_num_threads(os.cpu_count())
-cfg = O.PAPER
-M, T, SEED_W, SEED_X, NS = 3, 32000, 0, 1234, 64
-sd = O.init_state_dict(cfg, SEED_W)
-mix, src, lens = O.synthetic_batch(M, T, cfg.C, cfg.L, SEED_X)
-sd64 = {k: v.double() for k, v in sd.items()}
-loss, est, grads, max_snr, reord = O.train_step_grads(cfg, sd64, mix.double(), src.double(), lens)
-arrays = dict(M=np.int64(M), T=np.int64(T), seed_w=np.int64(SEED_W), seed_x=np.int64(SEED_X), loss=np.float64(loss.item()),
-              max_snr=max_snr.numpy(), est_stride=np.int64(37), est_sub=est.numpy()[..., ::37].astype(np.float32),
-              est_abs_max=np.float64(est.abs().max().item()), names=np.array(list(grads.keys())))
-gn, gmax, samp = [], [], []
-for k, g in grads.items():
-    f = g.flatten()
-    idx = torch.linspace(0, f.numel() - 1, NS).long()
-    gn.append(f.norm().item())
-    gmax.append(f.abs().max().item())
-    samp.append(f[idx].numpy())
-arrays.update(g_norm=np.array(gn), g_absmax=np.array(gmax), g_samples=np.stack(samp))
-out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "paper_cfg2_fp64.npz")
-np.savez_compressed(out, **arrays)
-print(out, os.path.getsize(out) // 1024, "KiB")
+NS = 2048
+
+
+def sample_index(numel):
+    return torch.arange(numel) if numel <= 4096 else torch.linspace(0, numel - 1, NS).long()
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.PAPER
+    M, T, SEED_W, SEED_X = 3, 32000, 0, 1234
+    sd = O.init_state_dict(cfg, SEED_W)
+    mix, src, lens = O.synthetic_batch(M, T, cfg.C, cfg.L, SEED_X)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    loss, est, grads, max_snr, reord = O.train_step_grads(cfg, sd64, mix.double(), src.double(), lens)
+    loss32, est32, grads32, _, _ = O.train_step_grads(cfg, sd, mix, src, lens)
+    arrays = dict(M=np.int64(M), T=np.int64(T), seed_w=np.int64(SEED_W), seed_x=np.int64(SEED_X),
+                  loss=np.float64(loss.item()), max_snr=max_snr.numpy(), est_stride=np.int64(37),
+                  est_sub=est.numpy()[..., ::37].astype(np.float32), est_abs_max=np.float64(est.abs().max().item()),
+                  names=np.array(list(grads.keys())))
+    gn, ref_err, samp = [], [], []
+    for k, g in grads.items():
+        f = g.flatten()
+        idx = sample_index(f.numel())
+        gn.append(f.norm().item())
+        s64, s32 = f[idx], grads32[k].flatten()[idx].double()
+        ref_err.append(((s32 - s64).norm() / s64.norm()).item())
+        samp.append(s64.numpy().astype(np.float32))
+    arrays.update(g_norm=np.array(gn), ref32_rel_l2=np.array(ref_err), g_samples=np.concatenate(samp),
+                  g_sample_counts=np.array([len(s) for s in samp]))
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "paper_cfg2_fp64.npz")
+    np.savez_compressed(out, **arrays)
+    print(out, os.path.getsize(out) // 1024, "KiB; worst fp32-oracle rel-L2 error", max(ref_err))
