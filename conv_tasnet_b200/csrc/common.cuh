@@ -112,6 +112,10 @@ struct GemmArgs {
   const float* res;        // residual [F, O] or nullptr
   double* stat_out;        // [M][2] accumulates stats of prelu(acc, alpha_out) or nullptr
   const float* alpha_out;
+  // bf16 hi/lo planes of the weight as an [O, Kd] row-major (K-major) matrix, for the tcgen05 path; when null the
+  // standalone entry points split W into a library-owned scratch first
+  const void* W_hi;
+  const void* W_lo;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t s);
 

@@ -1,0 +1,690 @@
+// gemm_tc.cu — the 1x1 convolutions on Blackwell tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// fp32 parity on bf16 tensor cores: every fp32 operand x is split as x = hi + lo (+ O(2^-17 x)), hi = bf16(x),
+// lo = bf16(x - hi), and the product is accumulated in fp32 (TMEM) as hi*hi + lo*hi + hi*lo ("bf16x3").  Measured
+// end to end on the paper config: 7.7e-6 max-rel-err vs fp64 (budget 1e-4); plain TF32 gives 1.4e-3 and fails.
+//
+// forward / dgrad kernel (tc_gemm_kernel):   D[f, o] = epi( sum_c pro(A[f, c]) * W[o, c] )
+//   MMA M = 128 output channels (weights, K-major, pre-split bf16 hi/lo planes, loaded by TMA with 128B swizzle)
+//   MMA N = NF frames (16..256, chosen at launch to fill whole waves of 148 SMs)
+//   activations are fp32 in HBM: 8 converter warps load them (coalesced 16 B), apply the prologue (PReLU), split to
+//   bf16 hi/lo and write the 128B-swizzled K-major UMMA layout; the same warps run the epilogue from TMEM
+//   (tcgen05.ld 32x32b): lane = output channel, column = frame, so every store is a 128 B line.
+//   epilogues: norm fold (r*acc + c1 - mu*r*c2), residual add, gLN statistics of prelu(out) (fp64 atomics).
+// weight-gradient kernel (tc_wgrad_kernel):  dW[o, i] += sum_f G[f, o] * act(f, i)     (split over f)
+//   both operands are MN-major (the reduction index f is the slow one): converter warps write the MN-major
+//   128B-swizzled layout, optionally applying gamma*(prelu(z)-mu)*r+beta on the fly.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ctn {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every MMA issued so far by this thread has finished (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// instruction descriptor for kind::f16: bf16 x bf16 -> f32  (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// fp32 x8 -> bf16 hi x8 + bf16 lo x8 (round to nearest even both times)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+constexpr int TC_THREADS = 384;       // 4 control warps + 8 converter/epilogue warps
+constexpr int CONV_THREADS = 256;
+constexpr int BM = 128;               // MMA M (output channels)
+constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int W_PLANE_BYTES = BM * BK * 2;  // 16 KB
+
+struct TcGemmArgs {
+  const float* A;  // [F, Kd] fp32
+  float* D;        // [F, O]
+  int64_t F;
+  int O, Kd, K, NF;
+  const float* alpha_in;
+  const float* c1;
+  const float* c2;
+  NormStats st;
+  const float* res;
+  double* stat_out;
+  const float* alpha_out;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad GEMM
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcGemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (1024-byte aligned): per stage [W_hi | W_lo | A_hi | A_lo]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NF = a.NF;
+  const int a_plane = NF * 128;
+  const int stage_bytes = 2 * W_PLANE_BYTES + 2 * a_plane;
+  uint8_t* tail = smem + STAGES * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_mu = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* s_r = s_mu + 256;
+  int* s_m = reinterpret_cast<int*>(s_r + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * NF;
+  const int o0 = blockIdx.y * BM;
+  const int nkb = a.Kd / BK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1 + CONV_THREADS);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc<256>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: weight hi/lo planes =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_expect_tx(full + s, 2 * W_PLANE_BYTES);
+        tma_load_2d(st, &map_hi, full + s, kb * BK, o0);
+        tma_load_2d(st + W_PLANE_BYTES, &map_lo, full + s, kb * BK, o0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, NF, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + s * stage_bytes);
+        const uint32_t w_hi = sb, w_lo = sb + W_PLANE_BYTES, a_hi = sb + 2 * W_PLANE_BYTES, a_lo = a_hi + a_plane;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes along the swizzled row
+          const uint64_t dwh = make_desc(w_hi + ko, 16, 1024), dwl = make_desc(w_lo + ko, 16, 1024);
+          const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+          umma_bf16(tmem_base, dwl, dah, idesc, (kb | k) != 0);  // lo*hi
+          umma_bf16(tmem_base, dwh, dal, idesc, 1);              // hi*lo
+          umma_bf16(tmem_base, dwh, dah, idesc, 1);              // hi*hi
+        }
+        umma_commit(empty + s);  // frees the stage when these MMAs have read it
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // ===== converters (fp32 -> bf16 hi/lo, swizzled K-major) then epilogue =====
+    const int t = threadIdx.x - 128;  // 0..255
+    const int chunk = t & 7, row0 = t >> 3;
+    const bool pro = a.alpha_in != nullptr;
+    const float alpha_in = pro ? __ldg(a.alpha_in) : 1.f;
+    // per-column (frame) metadata for the epilogue
+    if (t < NF) {
+      const int64_t f = f0 + t;
+      int m = -1;
+      float mu = 0.f, r = 1.f;
+      if (f < a.F) {
+        m = (int)(f / a.K);
+        if (a.c1 != nullptr) load_stats(a.st, m, f, mu, r);
+      }
+      s_m[t] = m;
+      s_mu[t] = mu;
+      s_r[t] = r;
+    }
+    const int nit = (NF + 31) / 32;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      float4 v[8][2];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (it < nit) {
+          const int r = row0 + it * 32;
+          const int64_t f = f0 + r;
+          if (r < NF && f < a.F) {
+            const float4* src = reinterpret_cast<const float4*>(a.A + f * a.Kd + kb * BK + chunk * 8);
+            v[it][0] = __ldg(src);
+            v[it][1] = __ldg(src + 1);
+          } else {
+            v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      mbar_wait(empty + s, ph ^ 1);
+      uint8_t* st = smem + s * stage_bytes + 2 * W_PLANE_BYTES;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (it < nit) {
+          const int r = row0 + it * 32;
+          if (r < NF) {
+            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+            if (pro) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(st + off) = hi;
+            *reinterpret_cast<uint4*>(st + a_plane + off) = lo;
+          }
+        }
+      }
+      fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
+      mbar_arrive(full + s);
+    }
+
+    // ---- epilogue ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // s_m / s_mu / s_r written by all converter threads
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int o = o0 + q * 32 + lane;
+    const int O = a.O;
+    const bool fold = a.c1 != nullptr, stats = a.stat_out != nullptr;
+    const float c1 = fold ? __ldg(a.c1 + o) : 0.f, c2 = fold ? __ldg(a.c2 + o) : 0.f;
+    const float alpha_out = (stats && a.alpha_out) ? __ldg(a.alpha_out) : 1.f;
+    const int jb = half * (NF / 2), je = jb + NF / 2;
+    float s1 = 0.f, s2 = 0.f;
+    int cur_m = -1;
+    for (int j = jb; j < je; j += 8) {
+      float acc[8];
+      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = s_m[j + i];
+        if (m < 0) continue;  // past the last frame (warp-uniform)
+        const int64_t f = f0 + j + i;
+        float val = acc[i];
+        if (fold) {
+          const float r = s_r[j + i], mr = s_mu[j + i] * r;
+          val = r * val + c1 - mr * c2;
+        }
+        if (a.res != nullptr) val += __ldg(a.res + f * O + o);
+        a.D[f * O + o] = val;
+        if (stats) {
+          if (m != cur_m) {
+            if (cur_m >= 0) {
+              const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+              if (lane == 0) {
+                atomicAdd(a.stat_out + 2 * cur_m, d1);
+                atomicAdd(a.stat_out + 2 * cur_m + 1, d2);
+              }
+            }
+            cur_m = m;
+            s1 = s2 = 0.f;
+          }
+          const float p = prelu(val, alpha_out);
+          s1 += p;
+          s2 = fmaf(p, p, s2);
+        }
+      }
+    }
+    if (stats && cur_m >= 0) {
+      const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+      if (lane == 0) {
+        atomicAdd(a.stat_out + 2 * cur_m, d1);
+        atomicAdd(a.stat_out + 2 * cur_m + 1, d2);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int WK = 32;       // f rows per stage
+constexpr int WSTAGES = 4;
+constexpr int WNI = 256;     // N tile (input channels); I must be a multiple of it or equal 128 (template below)
+
+struct TcWgradArgs {
+  const float* G;    // [F, O]
+  const float* Act;  // [F, I]
+  float* dW;         // [O, I]
+  int64_t F;
+  int O, I, K;
+  int f_chunk;
+  const float* alpha;
+  const float* gamma;
+  const float* beta;
+  NormStats st;
+};
+
+template <int NI>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_PLANE = WK * BM * 2;   // 8 KB   (2 groups of 64 o-columns x 32 rows x 128 B)
+  constexpr int B_PLANE = WK * NI * 2;   // 16 KB for NI = 256
+  constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  constexpr int GROUP = WK * 128;        // bytes of one 64-column group (LBO)
+  uint8_t* tail = smem + WSTAGES * STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + WSTAGES;
+  uint64_t* tmem_full = empty + WSTAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.x * BM, i0 = blockIdx.y * NI;
+  const int64_t fb = (int64_t)blockIdx.z * a.f_chunk;
+  const int64_t fe = fb + a.f_chunk < a.F ? fb + a.f_chunk : a.F;
+  const int nkb = fb < fe ? (int)((fe - fb + WK - 1) / WK) : 0;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WSTAGES; ++s) {
+      mbar_init(full + s, CONV_THREADS);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc<256>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (nkb > 0) {
+    if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(BM, NI, 1, 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + s * STAGE);
+          const uint32_t g_hi = sb, g_lo = sb + A_PLANE, x_hi = sb + 2 * A_PLANE, x_lo = x_hi + B_PLANE;
+#pragma unroll
+          for (int k = 0; k < WK / 16; ++k) {
+            const uint32_t ko = k * 16 * 128;  // 16 k-rows of 128 bytes
+            const uint64_t dgh = make_desc(g_hi + ko, GROUP, 1024), dgl = make_desc(g_lo + ko, GROUP, 1024);
+            const uint64_t dxh = make_desc(x_hi + ko, GROUP, 1024), dxl = make_desc(x_lo + ko, GROUP, 1024);
+            umma_bf16(tmem_base, dgl, dxh, idesc, (kb | k) != 0);
+            umma_bf16(tmem_base, dgh, dxl, idesc, 1);
+            umma_bf16(tmem_base, dgh, dxh, idesc, 1);
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(tmem_full);
+      }
+    } else if (warp >= 4) {
+      const int t = threadIdx.x - 128;
+      const bool norm = a.gamma != nullptr, hasp = a.alpha != nullptr;
+      const float alpha = hasp ? __ldg(a.alpha) : 1.f;
+      // G tile: 32 rows x 16 chunks (8 floats each): 2 chunks per thread (rows t/16 and t/16 + 16)
+      const int gc = t & 15, gr = t >> 4;
+      // Act tile: 32 rows x NI/8 chunks
+      constexpr int XC = NI / 8;              // chunks per row
+      constexpr int XR = CONV_THREADS / XC;   // rows covered per pass
+      constexpr int XIT = WK / XR;
+      const int xc = t % XC, xr = t / XC;
+      float gam[8], bet[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gam[i] = norm ? __ldg(a.gamma + i0 + xc * 8 + i) : 1.f;
+        bet[i] = norm ? __ldg(a.beta + i0 + xc * 8 + i) : 0.f;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
+        const int64_t fk = fb + (int64_t)kb * WK;
+        float4 gv[2][2], xv[XIT][2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int64_t f = fk + gr + it * 16;
+          if (f < fe) {
+            const float4* src = reinterpret_cast<const float4*>(a.G + f * a.O + o0 + gc * 8);
+            gv[it][0] = __ldg(src);
+            gv[it][1] = __ldg(src + 1);
+          } else {
+            gv[it][0] = gv[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < XIT; ++it) {
+          const int64_t f = fk + xr + it * XR;
+          if (f < fe) {
+            const float4* src = reinterpret_cast<const float4*>(a.Act + f * a.I + i0 + xc * 8);
+            xv[it][0] = __ldg(src);
+            xv[it][1] = __ldg(src + 1);
+          } else {
+            xv[it][0] = xv[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        mbar_wait(empty + s, ph ^ 1);
+        uint8_t* st = smem + s * STAGE;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int k = gr + it * 16;
+          const float x[8] = {gv[it][0].x, gv[it][0].y, gv[it][0].z, gv[it][0].w,
+                              gv[it][1].x, gv[it][1].y, gv[it][1].z, gv[it][1].w};
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int off = (gc >> 3) * GROUP + k * 128 + (((gc & 7) ^ (k & 7)) << 4);
+          *reinterpret_cast<uint4*>(st + off) = hi;
+          *reinterpret_cast<uint4*>(st + A_PLANE + off) = lo;
+        }
+#pragma unroll
+        for (int it = 0; it < XIT; ++it) {
+          const int k = xr + it * XR;
+          const int64_t f = fk + k;
+          float x[8] = {xv[it][0].x, xv[it][0].y, xv[it][0].z, xv[it][0].w,
+                        xv[it][1].x, xv[it][1].y, xv[it][1].z, xv[it][1].w};
+          if (f < fe) {
+            if (hasp) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha);
+            }
+            if (norm) {
+              float mu, r;
+              load_stats(a.st, (int)(f / a.K), f, mu, r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = gam[i] * (x[i] - mu) * r + bet[i];
+            }
+          }
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int off = (xc >> 3) * GROUP + k * 128 + (((xc & 7) ^ (k & 7)) << 4);
+          *reinterpret_cast<uint4*>(st + 2 * A_PLANE + off) = hi;
+          *reinterpret_cast<uint4*>(st + 2 * A_PLANE + B_PLANE + off) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(full + s);
+      }
+      // ---- epilogue: atomically add the partial tile ----
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int q = warp & 3, half = (warp - 4) >> 2;
+      const int o = o0 + q * 32 + lane;
+      const int jb = half * (NI / 2), je = jb + NI / 2;
+      for (int j = jb; j < je; j += 8) {
+        float acc[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
+        float* dst = a.dW + (int64_t)o * a.I + i0 + j;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, acc[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight planes: fp32 [R, C] -> bf16 hi / lo planes, optionally transposed to [C, R]; batched over blockIdx.z
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int R, int C, int64_t src_stride,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           int64_t dst_stride, int transpose) {
+  __shared__ float tile[32][33];
+  const float* s = src + (int64_t)blockIdx.z * src_stride;
+  __nv_bfloat16* h = hi + (int64_t)blockIdx.z * dst_stride;
+  __nv_bfloat16* l = lo + (int64_t)blockIdx.z * dst_stride;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? s[(int64_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    float v;
+    int64_t idx;
+    bool ok;
+    if (!transpose) {
+      const int r = r0 + i, c = c0 + tx;
+      v = tile[i][tx]; idx = (int64_t)r * C + c; ok = r < R && c < C;
+    } else {
+      const int c = c0 + i, r = r0 + tx;  // dst is [C, R]
+      v = tile[tx][i]; idx = (int64_t)c * R + r; ok = r < R && c < C;
+    }
+    if (ok) {
+      const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+      h[idx] = hv;
+      l[idx] = __float2bfloat16_rn(v - __bfloat162float(hv));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 plane [rows, cols] row-major -> tensor map with a [128 rows x 64 cols] box, 128-byte swizzle
+static int make_plane_map(CUtensorMap* map, const void* plane, int rows, int cols) {
+  EncodeTiledFn enc = get_encode();
+  CTN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(plane), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CTN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return 0;
+}
+
+static int pick_nf(int64_t F, int o_tiles) {
+  // frames per tile (multiple of 16, <= 256) minimising (waves * tile time) on 148 SMs
+  int best = 128;
+  double best_cost = 1e30;
+  for (int nf = 64; nf <= 256; nf += 16) {
+    const int64_t tiles = (F + nf - 1) / nf * o_tiles;
+    const int64_t waves = (tiles + 147) / 148;
+    const double cost = (double)waves * (nf + 40);  // + fixed per-tile overhead (prologue/epilogue)
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = nf;
+    }
+  }
+  return best;
+}
+
+static size_t tc_gemm_smem(int NF) {
+  return (size_t)STAGES * (2 * W_PLANE_BYTES + 2 * NF * 128) + (2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3 + 1024;
+}
+
+}  // namespace
+
+bool tc_gemm_eligible(const GemmArgs& a) {
+  return a.W_hi != nullptr && a.W_lo != nullptr && a.Kd % BK == 0 && a.O % BM == 0 && a.F >= 16;
+}
+
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
+  CUtensorMap mh, ml;
+  CTN_TRY(make_plane_map(&mh, g.W_hi, g.O, g.Kd));
+  CTN_TRY(make_plane_map(&ml, g.W_lo, g.O, g.Kd));
+  TcGemmArgs a;
+  a.A = g.A; a.D = g.D; a.F = g.F; a.O = g.O; a.Kd = g.Kd; a.K = g.K;
+  a.NF = pick_nf(g.F, g.O / BM);
+  a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
+  a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
+  const size_t smem = tc_gemm_smem(a.NF);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  CTN_REQUIRE(smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
+  dim3 grid(cdiv(g.F, a.NF), g.O / BM);
+  tc_gemm_kernel<<<grid, TC_THREADS, smem, s>>>(mh, ml, a);
+  return check_launch("tc_gemm_kernel");
+}
+
+bool tc_wgrad_eligible(const WgradArgs& a) {
+  return a.O % BM == 0 && (a.I % 256 == 0 || a.I == 128) && a.F >= 64;
+}
+
+int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
+  TcWgradArgs a;
+  a.G = w.G; a.Act = w.Act; a.dW = w.dW; a.F = w.F; a.O = w.O; a.I = w.I; a.K = w.K;
+  a.alpha = w.alpha; a.gamma = w.gamma; a.beta = w.beta; a.st = w.st;
+  const int ni = w.I % 256 == 0 ? 256 : 128;
+  const int tiles = (w.O / BM) * (w.I / ni);
+  int splits = (148 + tiles - 1) / tiles;
+  int f_chunk = (int)((w.F + splits - 1) / splits);
+  f_chunk = ((f_chunk + WK - 1) / WK) * WK;
+  splits = cdiv(w.F, f_chunk);
+  a.f_chunk = f_chunk;
+  dim3 grid(w.O / BM, w.I / ni, splits);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CTN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (ni == 256) {
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128 + 1024;
+    tc_wgrad_kernel<256><<<grid, TC_THREADS, smem, s>>>(a);
+  } else {
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128 + 1024;
+    tc_wgrad_kernel<128><<<grid, TC_THREADS, smem, s>>>(a);
+  }
+  return check_launch("tc_wgrad_kernel");
+}
+
+int run_split_planes(const float* src, int R, int C, int nb, int64_t src_stride, void* hi, void* lo, int64_t dst_stride,
+                     int transpose, cudaStream_t s) {
+  dim3 grid(cdiv(C, 32), cdiv(R, 32), nb);
+  split_planes_kernel<<<grid, 256, 0, s>>>(src, R, C, src_stride, reinterpret_cast<__nv_bfloat16*>(hi),
+                                           reinterpret_cast<__nv_bfloat16*>(lo), dst_stride, transpose);
+  return check_launch("split_planes_kernel");
+}
+
+}  // namespace ctn

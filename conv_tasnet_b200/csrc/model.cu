@@ -3,6 +3,7 @@
 // of kernel launches on one stream (graph-capturable: no allocation, no host sync, no host-side
 // data-dependent control flow).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -49,8 +50,59 @@ int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int
 int run_decoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, float*,
                     float*, float*, cudaStream_t);
 
-int launch_gemm(const GemmArgs& a, cudaStream_t s) { return launch_gemm_simt(a, s); }
-int launch_wgrad(const WgradArgs& a, cudaStream_t s) { return launch_wgrad_simt(a, s); }
+bool tc_gemm_eligible(const GemmArgs& a);
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
+bool tc_wgrad_eligible(const WgradArgs& a);
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);
+int run_split_planes(const float*, int, int, int, int64_t, void*, void*, int64_t, int, cudaStream_t);
+
+// CTN_FORCE_SIMT=1 routes every GEMM to the fp32 CUDA-core kernels (A/B debugging only; the default is tcgen05)
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTN_FORCE_SIMT");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// library-owned scratch for the standalone conv1x1 entry point (weight planes); the model path uses its workspace
+static int test_scratch(size_t bytes, void** out) {
+  static void* buf[16] = {nullptr};
+  static size_t cap[16] = {0};
+  int dev = 0;
+  CTN_CUDA(cudaGetDevice(&dev));
+  CTN_REQUIRE(dev < 16, "device index %d too large", dev);
+  if (cap[dev] < bytes) {
+    if (buf[dev]) CTN_CUDA(cudaFree(buf[dev]));
+    CTN_CUDA(cudaMalloc(&buf[dev], bytes));
+    cap[dev] = bytes;
+  }
+  *out = buf[dev];
+  return 0;
+}
+
+int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
+  if (force_simt() || a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) return launch_gemm_simt(a0, s);
+  GemmArgs a = a0;
+  if (a.W_hi == nullptr) {  // standalone call: split (and transpose if needed) the fp32 weight first
+    void* scr = nullptr;
+    const size_t plane = (size_t)a.O * a.Kd * 2;
+    CTN_TRY(test_scratch(2 * plane, &scr));
+    a.W_hi = scr;
+    a.W_lo = reinterpret_cast<char*>(scr) + plane;
+    if (a.w_is_kn)  // W is [Kd, O]: transpose to [O, Kd]
+      CTN_TRY(run_split_planes(a.W, a.Kd, a.O, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo), 0, 1, s));
+    else
+      CTN_TRY(run_split_planes(a.W, a.O, a.Kd, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo), 0, 0, s));
+  }
+  if (!tc_gemm_eligible(a)) return launch_gemm_simt(a0, s);
+  return launch_gemm_tc(a, s);
+}
+int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
+  if (force_simt() || !tc_wgrad_eligible(a)) return launch_wgrad_simt(a, s);
+  return launch_wgrad_tc(a, s);
+}
 
 // ---- flat parameter layout (reference state_dict order) -------------------------
 static inline int64_t al4(int64_t n) { return (n + 3) & ~(int64_t)3; }
@@ -110,6 +162,8 @@ struct Plan {
   // byte offsets
   int64_t w, rowstat0, x, z1, z2, gacc, rs1, rs2, score, Wbg, c1b, c2b, W2g, c1, c2;
   int64_t g, dn2, dn1, d_score, d_w, dn0, red;
+  int64_t pl_W1, pl_W2g, pl_Wbg, pl_Wm, pl_W1T, pl_W2T, pl_WbT, pl_WmT;  // bf16 hi planes; lo plane follows at +pl_lo
+  int64_t pl_lo;
   int64_t x_stride, z_stride, rs_stride;  // bytes between consecutive blocks' buffers (0 when not stashed)
   int64_t total;
 };
@@ -146,6 +200,21 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
   p.W2g = take((int64_t)p.nblk * c.B * c.H * 4);
   p.c1 = take((int64_t)p.nblk * c.B * 4);
   p.c2 = take((int64_t)p.nblk * c.B * 4);
+  {  // bf16 hi/lo weight planes for the tcgen05 GEMMs: one region of hi planes, an identical region of lo planes
+    const int64_t start = o;
+    p.pl_W1 = take((int64_t)p.nblk * c.H * c.B * 2);
+    p.pl_W2g = take((int64_t)p.nblk * c.B * c.H * 2);
+    p.pl_Wbg = take((int64_t)c.B * c.N * 2);
+    p.pl_Wm = take((int64_t)c.C * c.N * c.B * 2);
+    if (training) {
+      p.pl_W1T = take((int64_t)p.nblk * c.H * c.B * 2);
+      p.pl_W2T = take((int64_t)p.nblk * c.B * c.H * 2);
+      p.pl_WbT = take((int64_t)c.B * c.N * 2);
+      p.pl_WmT = take((int64_t)c.C * c.N * c.B * 2);
+    }
+    p.pl_lo = o - start;
+    o += p.pl_lo;
+  }
   if (training) {
     p.g = take(2 * al256(F * c.B * 4));
     p.dn2 = take(F * c.H * 4);
@@ -218,6 +287,15 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
                             X.at<float>(p.c1b), X.at<float>(p.c2b), 0, 0, s));
   CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
                             X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
+  // bf16 hi/lo planes of every GEMM weight (batched over the blocks)
+  CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
+                           X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, 0, s));
+  CTN_TRY(run_split_planes(X.at<float>(p.W2g), c.B, c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
+                           X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, 0, s));
+  CTN_TRY(run_split_planes(X.at<float>(p.Wbg), c.B, c.N, 1, 0, X.at<char>(p.pl_Wbg), X.at<char>(p.pl_Wbg + p.pl_lo), 0,
+                           0, s));
+  CTN_TRY(run_split_planes(X.params + L.Wm, c.C * c.N, c.B, 1, 0, X.at<char>(p.pl_Wm), X.at<char>(p.pl_Wm + p.pl_lo), 0,
+                           0, s));
   // encoder + first cLN statistics + bottleneck (cLN folded into the GEMM epilogue)
   float* w = X.at<float>(p.w);
   CTN_TRY(run_encoder_fwd(mixture, X.params + L.U, M, p.T, c.N, c.L, w, s));
@@ -227,6 +305,7 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
     a.A = w; a.W = X.at<float>(p.Wbg); a.D = X.x(0); a.F = F; a.O = c.B; a.Kd = c.N; a.K = K;
     a.c1 = X.at<float>(p.c1b); a.c2 = X.at<float>(p.c2b);
     a.st.row = X.at<float>(p.rowstat0);
+    a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo);
     CTN_TRY(launch_gemm(a, s));
   }
   for (int b = 0; b < nblk; ++b) {
@@ -235,6 +314,8 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       GemmArgs a = {};
       a.A = X.x(b); a.W = X.blk(b, L.W1); a.D = X.z1(b); a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
       a.stat_out = X.stat_out(b, 0); a.alpha_out = X.blk(b, L.a1);
+      a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * 2;
+      a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * 2;
       CTN_TRY(launch_gemm(a, s));
     }
     if (!gln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
@@ -249,12 +330,15 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.c1 = X.at<float>(p.c1) + (int64_t)b * c.B; a.c2 = X.at<float>(p.c2) + (int64_t)b * c.B;
       a.st = X.stats(b, 1);
       a.res = X.x(b);
+      a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * 2;
+      a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * 2;
       CTN_TRY(launch_gemm(a, s));
     }
   }
   {  // mask conv
     GemmArgs a = {};
     a.A = X.x(nblk); a.W = X.params + L.Wm; a.D = X.at<float>(p.score); a.F = F; a.O = c.C * c.N; a.Kd = c.B; a.K = K;
+    a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo);
     CTN_TRY(launch_gemm(a, s));
   }
   return run_decoder_fwd(X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
@@ -286,6 +370,15 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
   float* g_cur = g_buf[0];
   if (!accumulate) CTN_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * 4, s));
   CTN_CUDA(cudaMemsetAsync(X.at<char>(p.red), 0, (size_t)(nblk * 2 + 1) * M * 2 * 8, s));
+  // transposed bf16 hi/lo weight planes for the data-gradient GEMMs
+  CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1T),
+                           X.at<char>(p.pl_W1T + p.pl_lo), (int64_t)c.H * c.B, 1, s));
+  CTN_TRY(run_split_planes(X.blk(0, L.W2), c.B, c.H, nblk, L.blk_stride, X.at<char>(p.pl_W2T),
+                           X.at<char>(p.pl_W2T + p.pl_lo), (int64_t)c.B * c.H, 1, s));
+  CTN_TRY(run_split_planes(X.params + L.Wb, c.B, c.N, 1, 0, X.at<char>(p.pl_WbT), X.at<char>(p.pl_WbT + p.pl_lo), 0, 1,
+                           s));
+  CTN_TRY(run_split_planes(X.params + L.Wm, c.C * c.N, c.B, 1, 0, X.at<char>(p.pl_WmT), X.at<char>(p.pl_WmT + p.pl_lo),
+                           0, 1, s));
   CTN_TRY(run_decoder_bwd(d_est, X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
                           c.mask_nonlinear == CTN_MASK_SOFTMAX, d_score, d_w, grads + L.V, s));
   {  // mask conv: dWm, g = d_score Wm
@@ -294,6 +387,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     CTN_TRY(launch_wgrad(wa, s));
     GemmArgs a = {};
     a.A = d_score; a.W = X.params + L.Wm; a.w_is_kn = 1; a.D = g_cur; a.F = F; a.O = c.B; a.Kd = c.C * c.N; a.K = K;
+    a.W_hi = X.at<char>(p.pl_WmT); a.W_lo = X.at<char>(p.pl_WmT + p.pl_lo);
     CTN_TRY(launch_gemm(a, s));
   }
   }
@@ -308,6 +402,8 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     {  // dn2 = g W2
       GemmArgs a = {};
       a.A = g_cur; a.W = X.blk(b, L.W2); a.w_is_kn = 1; a.D = dn2; a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
+      a.W_hi = X.at<char>(p.pl_W2T) + (int64_t)b * c.B * c.H * 2;
+      a.W_lo = X.at<char>(p.pl_W2T + p.pl_lo) + (int64_t)b * c.B * c.H * 2;
       CTN_TRY(launch_gemm(a, s));
     }
     {  // dW2 = g^T norm2(prelu(z2))
@@ -333,6 +429,8 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     {  // g_prev = g + dz1 W1
       GemmArgs a = {};
       a.A = dn1; a.W = X.blk(b, L.W1); a.w_is_kn = 1; a.D = g_nxt; a.F = F; a.O = c.B; a.Kd = c.H; a.K = K;
+      a.W_hi = X.at<char>(p.pl_W1T) + (int64_t)b * c.H * c.B * 2;
+      a.W_lo = X.at<char>(p.pl_W1T + p.pl_lo) + (int64_t)b * c.H * c.B * 2;
       a.res = g_cur;
       CTN_TRY(launch_gemm(a, s));
     }
@@ -349,6 +447,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     CTN_TRY(launch_wgrad(wa, s));
     GemmArgs a = {};
     a.A = g_cur; a.W = X.params + L.Wb; a.w_is_kn = 1; a.D = dn0; a.F = F; a.O = c.N; a.Kd = c.B; a.K = K;
+    a.W_hi = X.at<char>(p.pl_WbT); a.W_lo = X.at<char>(p.pl_WbT + p.pl_lo);
     CTN_TRY(launch_gemm(a, s));
   }
   CTN_TRY(run_norm_bwd_reduce(dn0, w, nullptr, st0, X.params + L.g0, M, K, c.N, grads + L.g0, grads + L.b0, nullptr, s));

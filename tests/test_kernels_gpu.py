@@ -14,6 +14,7 @@ from oracle import fused_schedule as FS
 
 pytestmark = pytest.mark.gpu
 TOL_F, TOL_G = 1e-5, 1e-4
+TOL_TC = 2e-5  # 1x1 convs on tcgen05 use the bf16x3 split: per-GEMM error bound ~2^-16 (measured 5e-6)
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -66,8 +67,8 @@ def test_conv1x1_plain_and_stats(M, K, Kd, Ochan, kn):
     call("ctn_conv1x1", P(A), P(Wdev), kn, P(D), M * K, Ochan, Kd, K, None, None, None, None, None, None, P(stat),
          P(alpha_out))
     want = A.cpu().double() @ W.cpu().double().t()
-    assert rel_err(D.cpu(), want) < TOL_F
-    assert rel_err(stat.cpu(), gln_acc(FS.prelu(want, 0.21))) < TOL_F
+    assert rel_err(D.cpu(), want) < TOL_TC
+    assert rel_err(stat.cpu(), gln_acc(FS.prelu(want, 0.21))) < TOL_TC
 
 
 @pytest.mark.parametrize("norm", ["gLN", "cLN"])
@@ -89,7 +90,7 @@ def test_conv1x1_prelu_normfold_residual(norm, M, K, Kd, Ochan):
     mu_d, r_d = (FS.sample_stats(a) if norm == "gLN" else FS.row_stats(a))
     want = FS.gemm_normfold(a, mu_d, r_d, W.cpu().double(), gamma.cpu().double(), beta.cpu().double(),
                             res.cpu().double())
-    assert rel_err(D.cpu(), want) < TOL_F
+    assert rel_err(D.cpu(), want) < TOL_TC
 
 
 @pytest.mark.parametrize("norm", [None, "gLN", "cLN"])
