@@ -116,19 +116,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// fp32 x8 -> bf16 hi x8 + bf16 lo x8 (round to nearest even both times)
+// fp32 x8 -> bf16 hi x8 + bf16 lo x8 (round to nearest even both times), packed converts
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));  // first source -> upper half
+  return r;
+}
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    h[i] = cvt_bf16x2(x[2 * i], x[2 * i + 1]);
+    const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+    l[i] = cvt_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 constexpr int TC_THREADS = 384;       // 4 control warps + 8 converter/epilogue warps
@@ -142,7 +156,7 @@ struct TcGemmArgs {
   const float* A;  // [F, Kd] fp32
   float* D;        // [F, O]
   int64_t F;
-  int O, Kd, K, NF;
+  int O, Kd, K, NF, stages;
   const float* alpha_in;
   const float* c1;
   const float* c2;
@@ -155,22 +169,22 @@ struct TcGemmArgs {
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad GEMM
 // ------------------------------------------------------------------------------------------------
+// smem map (dynamic, 1024-byte aligned): NST stages of [W_hi 16K | W_lo 16K | A_hi NF*128 | A_lo NF*128], then
+// barriers, the TMEM base address, and per-column epilogue metadata float2 (r, mu*r) + int sample index.
+template <bool FOLD, bool RES, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcGemmArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (1024-byte aligned): per stage [W_hi | W_lo | A_hi | A_lo]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int NF = a.NF;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int NF = a.NF, NST = a.stages;
   const int a_plane = NF * 128;
   const int stage_bytes = 2 * W_PLANE_BYTES + 2 * a_plane;
-  uint8_t* tail = smem + STAGES * stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * stage_bytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* s_mu = reinterpret_cast<float*>(tmem_ptr + 2);
-  float* s_r = s_mu + 256;
-  int* s_m = reinterpret_cast<int*>(s_r + 256);
+  float2* s_col = reinterpret_cast<float2*>(tmem_ptr + 2);  // [256] (r, mu*r)
+  int* s_m = reinterpret_cast<int*>(s_col + 256);           // [256] sample index
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f0 = (int64_t)blockIdx.x * NF;
@@ -178,7 +192,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int nkb = a.Kd / BK;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full + s, 1 + CONV_THREADS);
       mbar_init(empty + s, 1);
     }
@@ -196,7 +211,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     // ===== TMA producer: weight hi/lo planes =====
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        const int s = kb % NST, ph = (kb / NST) & 1;
         mbar_wait(empty + s, ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(full + s, 2 * W_PLANE_BYTES);
@@ -209,10 +224,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, NF, 0, 0);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        const int s = kb % NST, ph = (kb / NST) & 1;
         mbar_wait(full + s, ph);
         tc_fence_after();
-        const uint32_t sb = smem_u32(smem + s * stage_bytes);
+        const uint32_t sb = smem_base + s * stage_bytes;
         const uint32_t w_hi = sb, w_lo = sb + W_PLANE_BYTES, a_hi = sb + 2 * W_PLANE_BYTES, a_lo = a_hi + a_plane;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
@@ -233,108 +248,127 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const int chunk = t & 7, row0 = t >> 3;
     const bool pro = a.alpha_in != nullptr;
     const float alpha_in = pro ? __ldg(a.alpha_in) : 1.f;
-    // per-column (frame) metadata for the epilogue
-    if (t < NF) {
-      const int64_t f = f0 + t;
+    const int nvalid = (int)(a.F - f0 < NF ? a.F - f0 : NF);  // frames of this tile that exist
+    if (t < NF) {  // per-column (frame) metadata for the epilogue
       int m = -1;
       float mu = 0.f, r = 1.f;
-      if (f < a.F) {
-        m = (int)(f / a.K);
-        if (a.c1 != nullptr) load_stats(a.st, m, f, mu, r);
+      if (t < nvalid) {
+        m = (int)((f0 + t) / a.K);
+        if (FOLD) load_stats(a.st, m, f0 + t, mu, r);
       }
       s_m[t] = m;
-      s_mu[t] = mu;
-      s_r[t] = r;
+      s_col[t] = make_float2(r, mu * r);
     }
     const int nit = (NF + 31) / 32;
+    const float* abase = a.A + (f0 + row0) * a.Kd + chunk * 8;
+    const int row_stride32 = 32 * a.Kd;  // floats between the rows of consecutive passes
+    const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 32*it keeps (row & 7)
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      const int s = kb % NST, ph = (kb / NST) & 1;
       float4 v[8][2];
+      const float* src = abase + kb * BK;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it < nit) {
-          const int r = row0 + it * 32;
-          const int64_t f = f0 + r;
-          if (r < NF && f < a.F) {
-            const float4* src = reinterpret_cast<const float4*>(a.A + f * a.Kd + kb * BK + chunk * 8);
-            v[it][0] = __ldg(src);
-            v[it][1] = __ldg(src + 1);
+          if (row0 + it * 32 < nvalid) {
+            v[it][0] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32));
+            v[it][1] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + 1);
           } else {
             v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
       }
       mbar_wait(empty + s, ph ^ 1);
-      uint8_t* st = smem + s * stage_bytes + 2 * W_PLANE_BYTES;
+      const uint32_t st = smem_base + s * stage_bytes + 2 * W_PLANE_BYTES + st_off;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        if (it < nit) {
-          const int r = row0 + it * 32;
-          if (r < NF) {
-            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
-            if (pro) {
+        if (it < nit && row0 + it * 32 < NF) {
+          float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+          if (pro) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
-            }
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(st + off) = hi;
-            *reinterpret_cast<uint4*>(st + a_plane + off) = lo;
+            for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
           }
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          sts128(st + it * 32 * 128, hi);
+          sts128(st + it * 32 * 128 + a_plane, lo);
         }
       }
       fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
       mbar_arrive(full + s);
     }
 
-    // ---- epilogue ----
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // s_m / s_mu / s_r written by all converter threads
+    // ---- epilogue: TMEM -> registers -> global; lane = output channel, column = frame ----
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // column metadata written by the converter threads
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int o = o0 + q * 32 + lane;
     const int O = a.O;
-    const bool fold = a.c1 != nullptr, stats = a.stat_out != nullptr;
-    const float c1 = fold ? __ldg(a.c1 + o) : 0.f, c2 = fold ? __ldg(a.c2 + o) : 0.f;
-    const float alpha_out = (stats && a.alpha_out) ? __ldg(a.alpha_out) : 1.f;
-    const int jb = half * (NF / 2), je = jb + NF / 2;
+    const float c1 = FOLD ? __ldg(a.c1 + o) : 0.f, c2 = FOLD ? __ldg(a.c2 + o) : 0.f;
+    const float alpha_out = (STATS && a.alpha_out) ? __ldg(a.alpha_out) : 1.f;
+    const int jb = half * (NF / 2);
+    const int je = min(jb + NF / 2, nvalid);
+    float* dptr = a.D + f0 * O + o;
+    const float* rptr = RES ? a.res + f0 * O + o : nullptr;
+    const uint32_t col_s = smem_u32(s_col);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
-    int cur_m = -1;
+    int cur_m = STATS && jb < je ? s_m[jb] : -1;
     for (int j = jb; j < je; j += 8) {
       float acc[8];
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
+      tmem_ld8(taddr + (uint32_t)j, acc);
+      const int nj = min(8, je - j);
+      const bool uniform = !STATS || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
+      if (nj == 8 && uniform) {  // fast path: whole chunk valid, one sample
+        float resv[8];
+        if (RES) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = s_m[j + i];
-        if (m < 0) continue;  // past the last frame (warp-uniform)
-        const int64_t f = f0 + j + i;
-        float val = acc[i];
-        if (fold) {
-          const float r = s_r[j + i], mr = s_mu[j + i] * r;
-          val = r * val + c1 - mr * c2;
+          for (int i = 0; i < 8; ++i) resv[i] = __ldg(rptr + (j + i) * O);
         }
-        if (a.res != nullptr) val += __ldg(a.res + f * O + o);
-        a.D[f * O + o] = val;
-        if (stats) {
-          if (m != cur_m) {
-            if (cur_m >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float val = acc[i];
+          if (FOLD) {
+            const float2 cm = lds64(col_s + (j + i) * 8);
+            val = fmaf(cm.x, val, fmaf(-cm.y, c2, c1));
+          }
+          if (RES) val += resv[i];
+          dptr[(j + i) * O] = val;
+          if (STATS) {
+            const float p = prelu(val, alpha_out);
+            s1 += p;
+            s2 = fmaf(p, p, s2);
+          }
+        }
+      } else {  // chunk crosses the end of the tile or a sample boundary (at most a couple per tile)
+        for (int i = 0; i < nj; ++i) {
+          float val = acc[i];
+          if (FOLD) {
+            const float2 cm = lds64(col_s + (j + i) * 8);
+            val = fmaf(cm.x, val, fmaf(-cm.y, c2, c1));
+          }
+          if (RES) val += __ldg(rptr + (j + i) * O);
+          dptr[(j + i) * O] = val;
+          if (STATS) {
+            const int m = s_m[j + i];
+            if (m != cur_m) {  // warp-uniform
               const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
               if (lane == 0) {
                 atomicAdd(a.stat_out + 2 * cur_m, d1);
                 atomicAdd(a.stat_out + 2 * cur_m + 1, d2);
               }
+              cur_m = m;
+              s1 = s2 = 0.f;
             }
-            cur_m = m;
-            s1 = s2 = 0.f;
+            const float p = prelu(val, alpha_out);
+            s1 += p;
+            s2 = fmaf(p, p, s2);
           }
-          const float p = prelu(val, alpha_out);
-          s1 += p;
-          s2 = fmaf(p, p, s2);
         }
       }
     }
-    if (stats && cur_m >= 0) {
+    if (STATS && cur_m >= 0) {
       const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
       if (lane == 0) {
         atomicAdd(a.stat_out + 2 * cur_m, d1);
@@ -369,8 +403,8 @@ struct TcWgradArgs {
 
 template <int NI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
   constexpr int A_PLANE = WK * BM * 2;   // 8 KB   (2 groups of 64 o-columns x 32 rows x 128 B)
   constexpr int B_PLANE = WK * NI * 2;   // 16 KB for NI = 256
   constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
@@ -388,6 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
   const int nkb = fb < fe ? (int)((fe - fb + WK - 1) / WK) : 0;
 
   if (warp == 1 && lane == 0) {
+    if (smem_base & 1023u) __trap();
     for (int s = 0; s < WSTAGES; ++s) {
       mbar_init(full + s, CONV_THREADS);
       mbar_init(empty + s, 1);
@@ -410,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
           mbar_wait(full + s, ph);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem + s * STAGE);
+          const uint32_t sb = smem_base + s * STAGE;
           const uint32_t g_hi = sb, g_lo = sb + A_PLANE, x_hi = sb + 2 * A_PLANE, x_lo = x_hi + B_PLANE;
 #pragma unroll
           for (int k = 0; k < WK / 16; ++k) {
@@ -469,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           }
         }
         mbar_wait(empty + s, ph ^ 1);
-        uint8_t* st = smem + s * STAGE;
+        const uint32_t st = smem_base + s * STAGE;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           const int k = gr + it * 16;
@@ -478,8 +513,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           uint4 hi, lo;
           split8(x, hi, lo);
           const int off = (gc >> 3) * GROUP + k * 128 + (((gc & 7) ^ (k & 7)) << 4);
-          *reinterpret_cast<uint4*>(st + off) = hi;
-          *reinterpret_cast<uint4*>(st + A_PLANE + off) = lo;
+          sts128(st + off, hi);
+          sts128(st + A_PLANE + off, lo);
         }
 #pragma unroll
         for (int it = 0; it < XIT; ++it) {
@@ -502,8 +537,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           uint4 hi, lo;
           split8(x, hi, lo);
           const int off = (xc >> 3) * GROUP + k * 128 + (((xc & 7) ^ (k & 7)) << 4);
-          *reinterpret_cast<uint4*>(st + 2 * A_PLANE + off) = hi;
-          *reinterpret_cast<uint4*>(st + 2 * A_PLANE + B_PLANE + off) = lo;
+          sts128(st + 2 * A_PLANE + off, hi);
+          sts128(st + 2 * A_PLANE + B_PLANE + off, lo);
         }
         fence_proxy_async();
         mbar_arrive(full + s);
@@ -518,8 +553,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         float acc[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
         float* dst = a.dW + (int64_t)o * a.I + i0 + j;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, acc[i]);
+        red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+        red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
       }
     }
   }
@@ -616,11 +651,19 @@ static int pick_nf(int64_t F, int o_tiles) {
   return best;
 }
 
-static size_t tc_gemm_smem(int NF) {
-  return (size_t)STAGES * (2 * W_PLANE_BYTES + 2 * NF * 128) + (2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3 + 1024;
+static int tc_gemm_stages(int NF) {
+  const size_t stage = 2 * W_PLANE_BYTES + 2 * (size_t)NF * 128;
+  const size_t budget = 227 * 1024 - ((2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3);
+  int st = (int)(budget / stage);
+  return st > STAGES ? STAGES : st;
+}
+static size_t tc_gemm_smem(int NF, int stages) {
+  return (size_t)stages * (2 * W_PLANE_BYTES + 2 * NF * 128) + (2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3;
 }
 
 }  // namespace
+
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
 
 bool tc_gemm_eligible(const GemmArgs& a) {
   return a.W_hi != nullptr && a.W_lo != nullptr && a.Kd % BK == 0 && a.O % BM == 0 && a.F >= 16;
@@ -635,15 +678,28 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   a.NF = pick_nf(g.F, g.O / BM);
   a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
   a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
-  const size_t smem = tc_gemm_smem(a.NF);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  CTN_REQUIRE(smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
+  a.stages = tc_gemm_stages(a.NF);
+  const size_t smem = tc_gemm_smem(a.NF, a.stages);
+  CTN_REQUIRE(a.stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
   dim3 grid(cdiv(g.F, a.NF), g.O / BM);
-  tc_gemm_kernel<<<grid, TC_THREADS, smem, s>>>(mh, ml, a);
+  const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
+#define CTN_TC_LAUNCH(FO, RE, ST)                                                                              \
+  do {                                                                                                         \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<FO, RE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    227 * 1024));                                                              \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    tc_gemm_kernel<FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, a);                                      \
+  } while (0)
+  if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false);
+  else if (!fold && !res && stats) CTN_TC_LAUNCH(false, false, true);
+  else if (!fold && res && !stats) CTN_TC_LAUNCH(false, true, false);
+  else if (fold && !res && !stats) CTN_TC_LAUNCH(true, false, false);
+  else if (fold && res && !stats) CTN_TC_LAUNCH(true, true, false);
+  else return launch_gemm_simt(g, s);  // combinations the model never issues
+#undef CTN_TC_LAUNCH
   return check_launch("tc_gemm_kernel");
 }
 
@@ -670,10 +726,10 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
     attr_set = true;
   }
   if (ni == 256) {
-    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128 + 1024;
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128;
     tc_wgrad_kernel<256><<<grid, TC_THREADS, smem, s>>>(a);
   } else {
-    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128 + 1024;
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128;
     tc_wgrad_kernel<128><<<grid, TC_THREADS, smem, s>>>(a);
   }
   return check_launch("tc_wgrad_kernel");
