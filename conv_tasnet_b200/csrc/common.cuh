@@ -13,6 +13,9 @@ namespace ctn {
 // ---- host-side error plumbing -----------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError -> 0 / 1 (+ message)
+// library-owned device scratch for the STANDALONE single-kernel entry points only (slot 0: weight planes, 1: partials);
+// the whole-model path never allocates: it uses the caller's workspace
+int lib_scratch(size_t bytes, void** out, int slot);
 
 #define CTN_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -116,6 +119,7 @@ struct GemmArgs {
   // standalone entry points split W into a library-owned scratch first
   const void* W_hi;
   const void* W_lo;
+  int tf32;  // 1: planes are fp32 (tf32 hi + exact remainder), forward precision; 0: bf16 hi/lo planes
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t s);
 

@@ -214,14 +214,15 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
 
 // backward: dn1[k] = sum_p Wd[p] * dz2[k - off_p];  dWd[p] += dz2[k - off_p] * n1[k];
 // plus the per-channel / per-sample reductions the norm1 backward needs (dgamma1, dbeta1, red1).
+// Per-channel sums leave the block as one row of `part` ([P+2][H]: taps, dgamma, dbeta) — no atomics; a second
+// kernel (reduce_partials_kernel) folds the rows.
 constexpr int DWB_TK = 16;
 template <int PT>
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict__ dz2, const float* __restrict__ z1,
                                                          const float* __restrict__ alpha1, NormStats st1,
                                                          const float* __restrict__ gamma1, const float* __restrict__ beta1,
                                                          const float* __restrict__ Wd, int K, int H, int P, int dil,
-                                                         int cshift, float* __restrict__ dn1, float* __restrict__ dWd,
-                                                         float* __restrict__ dgamma1, float* __restrict__ dbeta1,
+                                                         int cshift, float* __restrict__ dn1, float* __restrict__ part,
                                                          double* __restrict__ red1) {
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
@@ -237,61 +238,69 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
   }
   const float a1 = __ldg(alpha1);
   const int64_t base = (int64_t)m * K;
+  constexpr int NP_ = PT ? PT : MAXP;
+  const int PP = PT ? PT : P;
+  float* prow = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)(PP + 2) * H;
   double acc[2] = {0.0, 0.0};
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
-    constexpr int NP_ = PT ? PT : MAXP;
-    const int PP = PT ? PT : P;
-    float wd[4][NP_], dwd[4][NP_];
+    float wd[4][NP_];
+    float4 dwd[NP_];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int p = 0; p < NP_; ++p) {
 #pragma unroll
-      for (int p = 0; p < NP_; ++p) {
-        wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
-        dwd[j][p] = 0.f;
-      }
+      for (int j = 0; j < 4; ++j) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
+      dwd[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; ++kk) {
-      const int k = k0 + kk;
-      float mu, r;
-      if (st1.row != nullptr) {
-        const float2 v = reinterpret_cast<const float2*>(st1.row)[base + k];
-        mu = v.x; r = v.y;
-      } else {
-        mu = s_st.x; r = s_st.y;
-      }
-      const float4 a = prelu4(ld4(z1 + (base + k) * H + c), a1);
-      const float4 yh = make_float4((a.x - mu) * r, (a.y - mu) * r, (a.z - mu) * r, (a.w - mu) * r);
-      const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kk = 0; kk < nk; kk += 2) {
+      // issue every load of two frames first (ILP), then compute
+      float4 zv[2], tv[2][NP_];
+      float2 stv[2];
 #pragma unroll
-      for (int p = 0; p < NP_; ++p) {
-        const int ko = k - (p - cshift) * dil;  // the output frame whose tap p read input frame k
-        if (p >= PP || ko < 0 || ko >= K) continue;
-        const float4 v = ld4(dz2 + (base + ko) * H + c);
-        d.x = fmaf(wd[0][p], v.x, d.x); d.y = fmaf(wd[1][p], v.y, d.y);
-        d.z = fmaf(wd[2][p], v.z, d.z); d.w = fmaf(wd[3][p], v.w, d.w);
-        dwd[0][p] = fmaf(v.x, n1.x, dwd[0][p]); dwd[1][p] = fmaf(v.y, n1.y, dwd[1][p]);
-        dwd[2][p] = fmaf(v.z, n1.z, dwd[2][p]); dwd[3][p] = fmaf(v.w, n1.w, dwd[3][p]);
+      for (int u = 0; u < 2; ++u) {
+        const int k = k0 + kk + u;
+        const bool vk = kk + u < nk;
+        zv[u] = vk ? ld4(z1 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        stv[u] = (vk && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + k] : s_st;
+#pragma unroll
+        for (int p = 0; p < NP_; ++p) {
+          const int ko = k - (p - cshift) * dil;  // the output frame whose tap p read input frame k
+          tv[u][p] = (vk && p < PP && ko >= 0 && ko < K) ? ld4(dz2 + (base + ko) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      st4(dn1 + (base + k) * H + c, d);
-      dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
-      dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
-      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
-      const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-      s += (gh.x + gh.y) + (gh.z + gh.w);
-      s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (kk + u >= nk) break;
+        const int k = k0 + kk + u;
+        const float mu = stv[u].x, r = stv[u].y;
+        const float4 a = prelu4(zv[u], a1);
+        const float4 yh = make_float4((a.x - mu) * r, (a.y - mu) * r, (a.z - mu) * r, (a.w - mu) * r);
+        const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < NP_; ++p) {
+          const float4 v = tv[u][p];
+          d.x = fmaf(wd[0][p], v.x, d.x); d.y = fmaf(wd[1][p], v.y, d.y);
+          d.z = fmaf(wd[2][p], v.z, d.z); d.w = fmaf(wd[3][p], v.w, d.w);
+          dwd[p].x = fmaf(v.x, n1.x, dwd[p].x); dwd[p].y = fmaf(v.y, n1.y, dwd[p].y);
+          dwd[p].z = fmaf(v.z, n1.z, dwd[p].z); dwd[p].w = fmaf(v.w, n1.w, dwd[p].w);
+        }
+        st4(dn1 + (base + k) * H + c, d);
+        dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+        dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+        db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+        const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s += (gh.x + gh.y) + (gh.z + gh.w);
+        s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int p = 0; p < NP_; ++p)
-        if (p < PP) atomicAdd(dWd + (c + j) * PP + p, dwd[j][p]);
-    atomicAdd(dgamma1 + c + 0, dg.x); atomicAdd(dgamma1 + c + 1, dg.y);
-    atomicAdd(dgamma1 + c + 2, dg.z); atomicAdd(dgamma1 + c + 3, dg.w);
-    atomicAdd(dbeta1 + c + 0, db.x); atomicAdd(dbeta1 + c + 1, db.y);
-    atomicAdd(dbeta1 + c + 2, db.z); atomicAdd(dbeta1 + c + 3, db.w);
+    for (int p = 0; p < NP_; ++p)
+      if (p < PP) st4(prow + (int64_t)p * H + c, dwd[p]);
+    st4(prow + (int64_t)PP * H + c, dg);
+    st4(prow + (int64_t)(PP + 1) * H + c, db);
     acc[0] += (double)s;
     acc[1] += (double)s2;
   }
@@ -304,16 +313,41 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
   }
 }
 
+// fold `nb` partial rows of [Q][H] floats: q < P -> dW[c*P + q], q == P -> dgamma[c], q == P+1 -> dbeta[c]
+// grid (ceil(Q*H / 256), splits); each block sums a slice of the rows and adds it atomically (few atomics per output)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nb, int H, int P,
+                                                              float* __restrict__ dW, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta) {
+  const int n = (P + 2) * H;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int per = (nb + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(nb, b0 + per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = b0;
+  for (; b + 3 < b1; b += 4) {
+    s0 += part[(int64_t)b * n + i];
+    s1 += part[(int64_t)(b + 1) * n + i];
+    s2 += part[(int64_t)(b + 2) * n + i];
+    s3 += part[(int64_t)(b + 3) * n + i];
+  }
+  for (; b < b1; ++b) s0 += part[(int64_t)b * n + i];
+  const float v = (s0 + s1) + (s2 + s3);
+  const int q = i / H, c = i - q * H;
+  if (q < P) atomicAdd(dW + c * P + q, v);
+  else if (q == P) atomicAdd(dgamma + c, v);
+  else atomicAdd(dbeta + c, v);
+}
+
 // ---------------------------------------------------------------------------------------
-// norm backward, reduction pass: dgamma[c] += sum dn*yhat, dbeta[c] += sum dn,
-// red[m] += (sum dn*gamma, sum dn*gamma*yhat)
+// norm backward, reduction pass: per-channel sums (dn*yhat, dn) leave the block as a [2][Ch] row of `part`
+// (folded by reduce_partials_kernel with P = 0); red[m] += (sum dn*gamma, sum dn*gamma*yhat)
 // ---------------------------------------------------------------------------------------
-constexpr int NR_TK = 32;
+constexpr int NR_TK = 16;
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ dn, const float* __restrict__ z,
                                                               const float* __restrict__ alpha, NormStats st,
                                                               const float* __restrict__ gamma, int K, int Ch,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              double* __restrict__ redout) {
+                                                              float* __restrict__ part, double* __restrict__ redout) {
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
   const int m = blockIdx.y, k0 = blockIdx.x * NR_TK;
@@ -329,35 +363,40 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
   const bool hasp = alpha != nullptr;
   const float a = hasp ? __ldg(alpha) : 1.f;
   const int64_t base = (int64_t)m * K;
+  float* prow = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)2 * Ch;
   double acc[2] = {0.0, 0.0};
   for (int c = threadIdx.x * 4; c < Ch; c += blockDim.x * 4) {
     const float4 g = ld4(gamma + c);
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; ++kk) {
-      const int64_t f = base + k0 + kk;
-      float mu, r;
-      if (st.row != nullptr) {
-        const float2 v = reinterpret_cast<const float2*>(st.row)[f];
-        mu = v.x; r = v.y;
-      } else {
-        mu = s_st.x; r = s_st.y;
+    for (int kk = 0; kk < nk; kk += 4) {
+      float4 zv[4], dv[4];
+      float2 stv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool vk = kk + u < nk;
+        const int64_t f = base + k0 + kk + u;
+        zv[u] = vk ? ld4(z + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dv[u] = vk ? ld4(dn + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        stv[u] = (vk && st.row != nullptr) ? reinterpret_cast<const float2*>(st.row)[f] : s_st;
       }
-      float4 v = ld4(z + f * Ch + c);
-      if (hasp) v = prelu4(v, a);
-      const float4 d = ld4(dn + f * Ch + c);
-      const float4 yh = make_float4((v.x - mu) * r, (v.y - mu) * r, (v.z - mu) * r, (v.w - mu) * r);
-      dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
-      dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
-      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
-      const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-      s += (gh.x + gh.y) + (gh.z + gh.w);
-      s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk + u >= nk) break;
+        const float mu = stv[u].x, r = stv[u].y;
+        const float4 v = hasp ? prelu4(zv[u], a) : zv[u];
+        const float4 d = dv[u];
+        const float4 yh = make_float4((v.x - mu) * r, (v.y - mu) * r, (v.z - mu) * r, (v.w - mu) * r);
+        dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+        dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+        db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+        const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s += (gh.x + gh.y) + (gh.z + gh.w);
+        s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+      }
     }
-    atomicAdd(dgamma + c + 0, dg.x); atomicAdd(dgamma + c + 1, dg.y);
-    atomicAdd(dgamma + c + 2, dg.z); atomicAdd(dgamma + c + 3, dg.w);
-    atomicAdd(dbeta + c + 0, db.x); atomicAdd(dbeta + c + 1, db.y);
-    atomicAdd(dbeta + c + 2, db.z); atomicAdd(dbeta + c + 3, db.w);
+    st4(prow + c, dg);
+    st4(prow + Ch + c, db);
     acc[0] += (double)s;
     acc[1] += (double)s2;
   }
@@ -371,14 +410,15 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 }
 
 // apply pass, gLN: dz = r*(dn*gamma - m1 - yhat*m2) * prelu'(z); dalpha += sum da * z * [z<=0]
+constexpr int GA_TK = 8;
 __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
                                                             const float* __restrict__ alpha, NormStats st,
                                                             const float* __restrict__ gamma, const double* __restrict__ redin,
                                                             int K, int Ch, float* __restrict__ dalpha) {
   __shared__ double red[32];
   __shared__ float4 s_st;
-  const int m = blockIdx.y, k0 = blockIdx.x * NR_TK;
-  const int nk = min(NR_TK, K - k0);
+  const int m = blockIdx.y, k0 = blockIdx.x * GA_TK;
+  const int nk = min(GA_TK, K - k0);
   if (threadIdx.x == 0) {
     float mu, r;
     load_stats(st, m, 0, mu, r);
@@ -394,22 +434,33 @@ __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ 
   for (int c = threadIdx.x * 4; c < Ch; c += blockDim.x * 4) {
     const float4 g = ld4(gamma + c);
     float s = 0.f;
-    for (int kk = 0; kk < nk; ++kk) {
-      const int64_t f = base + k0 + kk;
-      const float4 zz = ld4(z + f * Ch + c);
-      const float4 v = hasp ? prelu4(zz, a) : zz;
-      const float4 d = ld4(dn + f * Ch + c);
-      float4 da;
-      da.x = r * (d.x * g.x - m1 - (v.x - mu) * r * m2);
-      da.y = r * (d.y * g.y - m1 - (v.y - mu) * r * m2);
-      da.z = r * (d.z * g.z - m1 - (v.z - mu) * r * m2);
-      da.w = r * (d.w * g.w - m1 - (v.w - mu) * r * m2);
-      if (hasp) {
-        s += (zz.x > 0.f ? 0.f : da.x * zz.x) + (zz.y > 0.f ? 0.f : da.y * zz.y) +
-             (zz.z > 0.f ? 0.f : da.z * zz.z) + (zz.w > 0.f ? 0.f : da.w * zz.w);
-        da.x *= dprelu(zz.x, a); da.y *= dprelu(zz.y, a); da.z *= dprelu(zz.z, a); da.w *= dprelu(zz.w, a);
+    for (int kk = 0; kk < nk; kk += 4) {
+      float4 zv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool vk = kk + u < nk;
+        const int64_t f = base + k0 + kk + u;
+        zv[u] = vk ? ld4(z + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dv[u] = vk ? ld4(dn + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      st4(dn + f * Ch + c, da);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk + u >= nk) break;
+        const int64_t f = base + k0 + kk + u;
+        const float4 zz = zv[u], d = dv[u];
+        const float4 v = hasp ? prelu4(zz, a) : zz;
+        float4 da;
+        da.x = r * (d.x * g.x - m1 - (v.x - mu) * r * m2);
+        da.y = r * (d.y * g.y - m1 - (v.y - mu) * r * m2);
+        da.z = r * (d.z * g.z - m1 - (v.z - mu) * r * m2);
+        da.w = r * (d.w * g.w - m1 - (v.w - mu) * r * m2);
+        if (hasp) {
+          s += (zz.x > 0.f ? 0.f : da.x * zz.x) + (zz.y > 0.f ? 0.f : da.y * zz.y) +
+               (zz.z > 0.f ? 0.f : da.z * zz.z) + (zz.w > 0.f ? 0.f : da.w * zz.w);
+          da.x *= dprelu(zz.x, a); da.y *= dprelu(zz.y, a); da.z *= dprelu(zz.z, a); da.w *= dprelu(zz.w, a);
+        }
+        st4(dn + f * Ch + c, da);
+      }
     }
     acc[0] += (double)s;
   }
@@ -684,27 +735,50 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
   return check_launch("dwconv_fwd_kernel");
 }
 
+static int fold_partials(const float* part, int nb, int H, int P, float* dW, float* dgamma, float* dbeta,
+                         cudaStream_t s) {
+  int splits = nb / 32;
+  splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
+  reduce_partials_kernel<<<dim3(cdiv((int64_t)(P + 2) * H, 256), splits), 256, 0, s>>>(part, nb, H, P, dW, dgamma, dbeta);
+  return check_launch("reduce_partials_kernel");
+}
+
+int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P) { return (int64_t)cdiv(K, DWB_TK) * M * (P + 2) * H; }
+int64_t norm_bwd_partial_floats(int M, int K, int Ch) { return (int64_t)cdiv(K, NR_TK) * M * 2 * Ch; }
+
 int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormStats st1, const float* gamma1,
                    const float* beta1, const float* Wd, int M, int K, int H, int P, int dil, int causal, float* dn1,
-                   float* dWd, float* dgamma1, float* dbeta1, double* red1, cudaStream_t s) {
+                   float* dWd, float* dgamma1, float* dbeta1, double* red1, float* part, cudaStream_t s) {
   CTN_REQUIRE(H % 4 == 0 && P >= 1 && P <= MAXP, "dwconv_bwd: bad H/P (%d/%d)", H, P);
+  if (part == nullptr) {  // standalone call: library-owned scratch
+    void* scr = nullptr;
+    CTN_TRY(lib_scratch((size_t)dwconv_bwd_partial_floats(M, K, H, P) * 4, &scr, 1));
+    part = reinterpret_cast<float*>(scr);
+  }
   const int cshift = causal ? P - 1 : (P - 1) / 2;
   const dim3 grid(cdiv(K, DWB_TK), M);
   if (P == 3)
     dwconv_bwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
-                                                               cshift, dn1, dWd, dgamma1, dbeta1, red1);
+                                                               cshift, dn1, part, red1);
   else
     dwconv_bwd_kernel<0><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
-                                                               cshift, dn1, dWd, dgamma1, dbeta1, red1);
-  return check_launch("dwconv_bwd_kernel");
+                                                               cshift, dn1, part, red1);
+  CTN_TRY(check_launch("dwconv_bwd_kernel"));
+  return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);
 }
 
 int run_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, NormStats st, const float* gamma, int M,
-                        int K, int Ch, float* dgamma, float* dbeta, double* red, cudaStream_t s) {
+                        int K, int Ch, float* dgamma, float* dbeta, double* red, float* part, cudaStream_t s) {
   CTN_REQUIRE(Ch % 4 == 0, "norm_bwd: channels must be a multiple of 4 (got %d)", Ch);
-  norm_bwd_reduce_kernel<<<dim3(cdiv(K, NR_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, K, Ch,
-                                                                                   dgamma, dbeta, red);
-  return check_launch("norm_bwd_reduce_kernel");
+  if (part == nullptr) {
+    void* scr = nullptr;
+    CTN_TRY(lib_scratch((size_t)norm_bwd_partial_floats(M, K, Ch) * 4, &scr, 1));
+    part = reinterpret_cast<float*>(scr);
+  }
+  const dim3 grid(cdiv(K, NR_TK), M);
+  norm_bwd_reduce_kernel<<<grid, block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, K, Ch, part, red);
+  CTN_TRY(check_launch("norm_bwd_reduce_kernel"));
+  return fold_partials(part, grid.x * grid.y, Ch, 0, nullptr, dgamma, dbeta, s);
 }
 
 int run_norm_bwd_apply(float* dn, const float* z, const float* alpha, NormStats st, const float* gamma,
@@ -715,7 +789,7 @@ int run_norm_bwd_apply(float* dn, const float* z, const float* alpha, NormStats 
                                                                dalpha);
     return check_launch("cln_bwd_apply_kernel");
   }
-  gln_bwd_apply_kernel<<<dim3(cdiv(K, NR_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, red, K, Ch,
+  gln_bwd_apply_kernel<<<dim3(cdiv(K, GA_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, red, K, Ch,
                                                                                  dalpha);
   return check_launch("gln_bwd_apply_kernel");
 }

@@ -1,8 +1,14 @@
 // gemm_tc.cu — the 1x1 convolutions on Blackwell tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// fp32 parity on bf16 tensor cores: every fp32 operand x is split as x = hi + lo (+ O(2^-17 x)), hi = bf16(x),
-// lo = bf16(x - hi), and the product is accumulated in fp32 (TMEM) as hi*hi + lo*hi + hi*lo ("bf16x3").  Measured
-// end to end on the paper config: 7.7e-6 max-rel-err vs fp64 (budget 1e-4); plain TF32 gives 1.4e-3 and fails.
+// fp32 parity on tensor cores by operand splitting: every fp32 operand x is split as x = hi + lo and the product is
+// accumulated in fp32 (TMEM) as lo*hi + hi*lo + hi*hi (3 MMAs).
+//   * forward 1x1 convs: TF32 split (hi = tf32(x), lo = x - hi exact; kind::tf32) -> 2.7e-7 max-rel-err end to end on
+//     the paper config, better than the reference's own fp32 (5.5e-7).  This matters beyond the 1e-4 output budget:
+//     forward rounding decides which pre-activations sit on the other side of a PReLU kink, and the gradient noise
+//     grows like sqrt(forward error) (see DESIGN.md "gradient parity").
+//   * data / weight gradients: bf16 split (hi = bf16(x), lo = bf16(x - hi); kind::f16) -> 5e-6 per GEMM, smooth
+//     error, half the tensor and shared-memory cost.
+//   Plain single-pass TF32 gives 1.4e-3 end to end and fails the 1e-4 budget.
 //
 // forward / dgrad kernel (tc_gemm_kernel):   D[f, o] = epi( sum_c pro(A[f, c]) * W[o, c] )
 //   MMA M = 128 output channels (weights, K-major, pre-split bf16 hi/lo planes, loaded by TMA with 128B swizzle)
@@ -85,6 +91,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives when every MMA issued so far by this thread has finished (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -111,9 +128,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 // instruction descriptor for kind::f16: bf16 x bf16 -> f32  (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, uint32_t fmt = 1) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp32 x4 -> tf32 hi x4 (round to nearest) + exact remainder lo x4 (the tensor core truncates lo to tf32: 2^-22 |x|)
+__device__ __forceinline__ void split4_tf32(const float4& x, uint4& hi, uint4& lo) {
+  uint32_t h[4];
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  float l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[i]) : "f"(xs[i]));
+    l[i] = xs[i] - __uint_as_float(h[i]);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(__float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
 }
 
 // fp32 x8 -> bf16 hi x8 + bf16 lo x8 (round to nearest even both times), packed converts
@@ -171,7 +202,7 @@ struct TcGemmArgs {
 // ------------------------------------------------------------------------------------------------
 // smem map (dynamic, 1024-byte aligned): NST stages of [W_hi 16K | W_lo 16K | A_hi NF*128 | A_lo NF*128], then
 // barriers, the TMEM base address, and per-column epilogue metadata float2 (r, mu*r) + int sample index.
-template <bool FOLD, bool RES, bool STATS>
+template <bool TF32, bool FOLD, bool RES, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -189,7 +220,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f0 = (int64_t)blockIdx.x * NF;
   const int o0 = blockIdx.y * BM;
-  const int nkb = a.Kd / BK;
+  constexpr int KB = TF32 ? 32 : 64;  // elements per 128-byte swizzle row = K extent of one stage
+  const int nkb = a.Kd / KB;
 
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
@@ -215,14 +247,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         mbar_wait(empty + s, ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(full + s, 2 * W_PLANE_BYTES);
-        tma_load_2d(st, &map_hi, full + s, kb * BK, o0);
-        tma_load_2d(st + W_PLANE_BYTES, &map_lo, full + s, kb * BK, o0);
+        tma_load_2d(st, &map_hi, full + s, kb * KB, o0);
+        tma_load_2d(st + W_PLANE_BYTES, &map_lo, full + s, kb * KB, o0);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, NF, 0, 0);
+      const uint32_t idesc = make_idesc(BM, NF, 0, 0, TF32 ? 2u : 1u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST, ph = (kb / NST) & 1;
         mbar_wait(full + s, ph);
@@ -230,13 +262,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         const uint32_t sb = smem_base + s * stage_bytes;
         const uint32_t w_hi = sb, w_lo = sb + W_PLANE_BYTES, a_hi = sb + 2 * W_PLANE_BYTES, a_lo = a_hi + a_plane;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes along the swizzled row
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t ko = k * 32;  // one MMA consumes 32 bytes of K per row (16 bf16 or 8 tf32)
           const uint64_t dwh = make_desc(w_hi + ko, 16, 1024), dwl = make_desc(w_lo + ko, 16, 1024);
           const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-          umma_bf16(tmem_base, dwl, dah, idesc, (kb | k) != 0);  // lo*hi
-          umma_bf16(tmem_base, dwh, dal, idesc, 1);              // hi*lo
-          umma_bf16(tmem_base, dwh, dah, idesc, 1);              // hi*hi
+          if (TF32) {
+            umma_tf32(tmem_base, dwl, dah, idesc, (kb | k) != 0);  // lo*hi
+            umma_tf32(tmem_base, dwh, dal, idesc, 1);              // hi*lo
+            umma_tf32(tmem_base, dwh, dah, idesc, 1);              // hi*hi
+          } else {
+            umma_bf16(tmem_base, dwl, dah, idesc, (kb | k) != 0);
+            umma_bf16(tmem_base, dwh, dal, idesc, 1);
+            umma_bf16(tmem_base, dwh, dah, idesc, 1);
+          }
         }
         umma_commit(empty + s);  // frees the stage when these MMAs have read it
       }
@@ -260,21 +298,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       s_col[t] = make_float2(r, mu * r);
     }
     const int nit = (NF + 31) / 32;
-    const float* abase = a.A + (f0 + row0) * a.Kd + chunk * 8;
+    constexpr int CE = TF32 ? 4 : 8;  // fp32 elements behind one 16-byte operand chunk
+    const float* abase = a.A + (f0 + row0) * a.Kd + chunk * CE;
     const int row_stride32 = 32 * a.Kd;  // floats between the rows of consecutive passes
     const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 32*it keeps (row & 7)
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NST, ph = (kb / NST) & 1;
       float4 v[8][2];
-      const float* src = abase + kb * BK;
+      const float* src = abase + kb * KB;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it < nit) {
           if (row0 + it * 32 < nvalid) {
             v[it][0] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32));
-            v[it][1] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + 1);
+            if (!TF32) v[it][1] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + 1);
           } else {
-            v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!TF32) v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
       }
@@ -283,13 +323,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it < nit && row0 + it * 32 < NF) {
-          float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
-          if (pro) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
-          }
           uint4 hi, lo;
-          split8(x, hi, lo);
+          if (TF32) {
+            float4 x = v[it][0];
+            if (pro) { x.x = prelu(x.x, alpha_in); x.y = prelu(x.y, alpha_in); x.z = prelu(x.z, alpha_in); x.w = prelu(x.w, alpha_in); }
+            split4_tf32(x, hi, lo);
+          } else {
+            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+            if (pro) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
+            }
+            split8(x, hi, lo);
+          }
           sts128(st + it * 32 * 128, hi);
           sts128(st + it * 32 * 128 + a_plane, lo);
         }
@@ -599,6 +645,23 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+// the TF32 flavour: hi = tf32(x) and the exact remainder, both stored as fp32 [R, C] planes (no transpose needed:
+// only the forward weights use it)
+__global__ void __launch_bounds__(256) split_planes_tf32_kernel(const float* __restrict__ src, int64_t n, int64_t src_stride,
+                                                                float* __restrict__ hi, float* __restrict__ lo,
+                                                                int64_t dst_stride) {
+  const float* s = src + (int64_t)blockIdx.y * src_stride;
+  float* h = hi + (int64_t)blockIdx.y * dst_stride;
+  float* l = lo + (int64_t)blockIdx.y * dst_stride;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = s[i];
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    h[i] = __uint_as_float(hb);
+    l[i] = v - __uint_as_float(hb);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -620,15 +683,17 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 plane [rows, cols] row-major -> tensor map with a [128 rows x 64 cols] box, 128-byte swizzle
-static int make_plane_map(CUtensorMap* map, const void* plane, int rows, int cols) {
+// weight plane [rows, cols] row-major (bf16, or fp32 for the TF32 flavour) -> tensor map with a
+// [128 rows x 128 bytes] box, 128-byte swizzle
+static int make_plane_map(CUtensorMap* map, const void* plane, int rows, int cols, bool tf32) {
   EncodeTiledFn enc = get_encode();
   CTN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  const cuuint32_t box[2] = {BK, BM};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * (tf32 ? 4 : 2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(tf32 ? 32 : 64), BM};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(plane), dims, strides, box, estr,
+  CUresult r = enc(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(plane), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CTN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -671,8 +736,9 @@ bool tc_gemm_eligible(const GemmArgs& a) {
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   CUtensorMap mh, ml;
-  CTN_TRY(make_plane_map(&mh, g.W_hi, g.O, g.Kd));
-  CTN_TRY(make_plane_map(&ml, g.W_lo, g.O, g.Kd));
+  const bool tf32 = g.tf32 != 0;
+  CTN_TRY(make_plane_map(&mh, g.W_hi, g.O, g.Kd, tf32));
+  CTN_TRY(make_plane_map(&ml, g.W_lo, g.O, g.Kd, tf32));
   TcGemmArgs a;
   a.A = g.A; a.D = g.D; a.F = g.F; a.O = g.O; a.Kd = g.Kd; a.K = g.K;
   a.NF = pick_nf(g.F, g.O / BM);
@@ -683,22 +749,27 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   CTN_REQUIRE(a.stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
   dim3 grid(cdiv(g.F, a.NF), g.O / BM);
   const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
-#define CTN_TC_LAUNCH(FO, RE, ST)                                                                              \
-  do {                                                                                                         \
-    static bool attr_set = false;                                                                              \
-    if (!attr_set) {                                                                                           \
-      CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<FO, RE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                    227 * 1024));                                                              \
-      attr_set = true;                                                                                         \
-    }                                                                                                          \
-    tc_gemm_kernel<FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, a);                                      \
+#define CTN_TC_LAUNCH(TF, FO, RE, ST)                                                                            \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TF, FO, RE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    227 * 1024));                                                                \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    tc_gemm_kernel<TF, FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, a);                                    \
   } while (0)
-  if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false);
-  else if (!fold && !res && stats) CTN_TC_LAUNCH(false, false, true);
-  else if (!fold && res && !stats) CTN_TC_LAUNCH(false, true, false);
-  else if (fold && !res && !stats) CTN_TC_LAUNCH(true, false, false);
-  else if (fold && res && !stats) CTN_TC_LAUNCH(true, true, false);
-  else return launch_gemm_simt(g, s);  // combinations the model never issues
+  if (tf32) {  // forward 1x1 convs
+    if (!fold && !res && !stats) CTN_TC_LAUNCH(true, false, false, false);
+    else if (!fold && !res && stats) CTN_TC_LAUNCH(true, false, false, true);
+    else if (fold && !res && !stats) CTN_TC_LAUNCH(true, true, false, false);
+    else if (fold && res && !stats) CTN_TC_LAUNCH(true, true, true, false);
+    else return launch_gemm_simt(g, s);  // combinations the model never issues
+  } else {     // data gradients
+    if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false);
+    else if (!fold && res && !stats) CTN_TC_LAUNCH(false, false, true, false);
+    else return launch_gemm_simt(g, s);
+  }
 #undef CTN_TC_LAUNCH
   return check_launch("tc_gemm_kernel");
 }
@@ -733,6 +804,14 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
     tc_wgrad_kernel<128><<<grid, TC_THREADS, smem, s>>>(a);
   }
   return check_launch("tc_wgrad_kernel");
+}
+
+int run_split_planes_tf32(const float* src, int64_t n, int nb, int64_t src_stride, void* hi, void* lo,
+                          int64_t dst_stride, cudaStream_t s) {
+  int gx = cdiv(n, 256 * 4);
+  split_planes_tf32_kernel<<<dim3(gx < 1 ? 1 : gx, nb), 256, 0, s>>>(src, n, src_stride, reinterpret_cast<float*>(hi),
+                                                                     reinterpret_cast<float*>(lo), dst_stride);
+  return check_launch("split_planes_tf32_kernel");
 }
 
 int run_split_planes(const float* src, int R, int C, int nb, int64_t src_stride, void* hi, void* lo, int64_t dst_stride,

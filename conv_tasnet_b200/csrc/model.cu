@@ -41,9 +41,11 @@ int run_prep_normfold(const float*, const float*, const float*, int, int, int, i
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
                    int, int, float*, double*, const float*, cudaStream_t);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
-                   int, int, int, int, int, float*, float*, float*, float*, double*, cudaStream_t);
+                   int, int, int, int, int, float*, float*, float*, float*, double*, float*, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
-                        float*, double*, cudaStream_t);
+                        float*, double*, float*, cudaStream_t);
+int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P);
+int64_t norm_bwd_partial_floats(int M, int K, int Ch);
 int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
                        float*, cudaStream_t);
 int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
@@ -55,6 +57,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 bool tc_wgrad_eligible(const WgradArgs& a);
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);
 int run_split_planes(const float*, int, int, int, int64_t, void*, void*, int64_t, int, cudaStream_t);
+int run_split_planes_tf32(const float*, int64_t, int, int64_t, void*, void*, int64_t, cudaStream_t);
 
 // CTN_FORCE_SIMT=1 routes every GEMM to the fp32 CUDA-core kernels (A/B debugging only; the default is tcgen05)
 static bool force_simt() {
@@ -66,19 +69,18 @@ static bool force_simt() {
   return v == 1;
 }
 
-// library-owned scratch for the standalone conv1x1 entry point (weight planes); the model path uses its workspace
-static int test_scratch(size_t bytes, void** out) {
-  static void* buf[16] = {nullptr};
-  static size_t cap[16] = {0};
+int lib_scratch(size_t bytes, void** out, int slot) {
+  static void* buf[16][2] = {{nullptr}};
+  static size_t cap[16][2] = {{0}};
   int dev = 0;
   CTN_CUDA(cudaGetDevice(&dev));
-  CTN_REQUIRE(dev < 16, "device index %d too large", dev);
-  if (cap[dev] < bytes) {
-    if (buf[dev]) CTN_CUDA(cudaFree(buf[dev]));
-    CTN_CUDA(cudaMalloc(&buf[dev], bytes));
-    cap[dev] = bytes;
+  CTN_REQUIRE(dev < 16 && slot >= 0 && slot < 2, "lib_scratch: bad device/slot");
+  if (cap[dev][slot] < bytes) {
+    if (buf[dev][slot]) CTN_CUDA(cudaFree(buf[dev][slot]));
+    CTN_CUDA(cudaMalloc(&buf[dev][slot], bytes));
+    cap[dev][slot] = bytes;
   }
-  *out = buf[dev];
+  *out = buf[dev][slot];
   return 0;
 }
 
@@ -87,14 +89,16 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
   GemmArgs a = a0;
   if (a.W_hi == nullptr) {  // standalone call: split (and transpose if needed) the fp32 weight first
     void* scr = nullptr;
-    const size_t plane = (size_t)a.O * a.Kd * 2;
-    CTN_TRY(test_scratch(2 * plane, &scr));
+    a.tf32 = a.w_is_kn ? 0 : 1;  // [O,Kd] weights = a forward conv (tf32 split); [Kd,O] = a data gradient (bf16 split)
+    const size_t plane = (size_t)a.O * a.Kd * (a.tf32 ? 4 : 2);
+    CTN_TRY(lib_scratch(2 * plane, &scr, 0));
     a.W_hi = scr;
     a.W_lo = reinterpret_cast<char*>(scr) + plane;
     if (a.w_is_kn)  // W is [Kd, O]: transpose to [O, Kd]
       CTN_TRY(run_split_planes(a.W, a.Kd, a.O, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo), 0, 1, s));
     else
-      CTN_TRY(run_split_planes(a.W, a.O, a.Kd, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo), 0, 0, s));
+      CTN_TRY(run_split_planes_tf32(a.W, (int64_t)a.O * a.Kd, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo),
+                                    0, s));
   }
   if (!tc_gemm_eligible(a)) return launch_gemm_simt(a0, s);
   return launch_gemm_tc(a, s);
@@ -161,7 +165,7 @@ struct Plan {
   int64_t F;
   // byte offsets
   int64_t w, rowstat0, x, z1, z2, gacc, rs1, rs2, score, Wbg, c1b, c2b, W2g, c1, c2;
-  int64_t g, dn2, dn1, d_score, d_w, dn0, red;
+  int64_t g, dn2, dn1, d_score, d_w, dn0, red, part;
   int64_t pl_W1, pl_W2g, pl_Wbg, pl_Wm, pl_W1T, pl_W2T, pl_WbT, pl_WmT;  // bf16 hi planes; lo plane follows at +pl_lo
   int64_t pl_lo;
   int64_t x_stride, z_stride, rs_stride;  // bytes between consecutive blocks' buffers (0 when not stashed)
@@ -202,10 +206,10 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
   p.c2 = take((int64_t)p.nblk * c.B * 4);
   {  // bf16 hi/lo weight planes for the tcgen05 GEMMs: one region of hi planes, an identical region of lo planes
     const int64_t start = o;
-    p.pl_W1 = take((int64_t)p.nblk * c.H * c.B * 2);
-    p.pl_W2g = take((int64_t)p.nblk * c.B * c.H * 2);
-    p.pl_Wbg = take((int64_t)c.B * c.N * 2);
-    p.pl_Wm = take((int64_t)c.C * c.N * c.B * 2);
+    p.pl_W1 = take((int64_t)p.nblk * c.H * c.B * 4);   // forward planes are fp32 (tf32 split)
+    p.pl_W2g = take((int64_t)p.nblk * c.B * c.H * 4);
+    p.pl_Wbg = take((int64_t)c.B * c.N * 4);
+    p.pl_Wm = take((int64_t)c.C * c.N * c.B * 4);
     if (training) {
       p.pl_W1T = take((int64_t)p.nblk * c.H * c.B * 2);
       p.pl_W2T = take((int64_t)p.nblk * c.B * c.H * 2);
@@ -223,6 +227,13 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
     p.d_w = take(F * c.N * 4);
     p.dn0 = take(F * c.N * 4);
     p.red = take((int64_t)(p.nblk * 2 + 1) * M * 2 * 8);
+    {
+      int64_t pf = dwconv_bwd_partial_floats(M, p.K, c.H, c.P);
+      const int64_t a = norm_bwd_partial_floats(M, p.K, c.H), b = norm_bwd_partial_floats(M, p.K, c.N);
+      pf = pf > a ? pf : a;
+      pf = pf > b ? pf : b;
+      p.part = take(pf * 4);
+    }
   }
   p.total = o;
   return p;
@@ -287,15 +298,15 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
                             X.at<float>(p.c1b), X.at<float>(p.c2b), 0, 0, s));
   CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
                             X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
-  // bf16 hi/lo planes of every GEMM weight (batched over the blocks)
-  CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
-                           X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, 0, s));
-  CTN_TRY(run_split_planes(X.at<float>(p.W2g), c.B, c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
-                           X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, 0, s));
-  CTN_TRY(run_split_planes(X.at<float>(p.Wbg), c.B, c.N, 1, 0, X.at<char>(p.pl_Wbg), X.at<char>(p.pl_Wbg + p.pl_lo), 0,
-                           0, s));
-  CTN_TRY(run_split_planes(X.params + L.Wm, c.C * c.N, c.B, 1, 0, X.at<char>(p.pl_Wm), X.at<char>(p.pl_Wm + p.pl_lo), 0,
-                           0, s));
+  // tf32 hi / exact-remainder planes of every forward GEMM weight (batched over the blocks)
+  CTN_TRY(run_split_planes_tf32(X.blk(0, L.W1), (int64_t)c.H * c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
+                                X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, s));
+  CTN_TRY(run_split_planes_tf32(X.at<float>(p.W2g), (int64_t)c.B * c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
+                                X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, s));
+  CTN_TRY(run_split_planes_tf32(X.at<float>(p.Wbg), (int64_t)c.B * c.N, 1, 0, X.at<char>(p.pl_Wbg),
+                                X.at<char>(p.pl_Wbg + p.pl_lo), 0, s));
+  CTN_TRY(run_split_planes_tf32(X.params + L.Wm, (int64_t)c.C * c.N * c.B, 1, 0, X.at<char>(p.pl_Wm),
+                                X.at<char>(p.pl_Wm + p.pl_lo), 0, s));
   // encoder + first cLN statistics + bottleneck (cLN folded into the GEMM epilogue)
   float* w = X.at<float>(p.w);
   CTN_TRY(run_encoder_fwd(mixture, X.params + L.U, M, p.T, c.N, c.L, w, s));
@@ -305,7 +316,7 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
     a.A = w; a.W = X.at<float>(p.Wbg); a.D = X.x(0); a.F = F; a.O = c.B; a.Kd = c.N; a.K = K;
     a.c1 = X.at<float>(p.c1b); a.c2 = X.at<float>(p.c2b);
     a.st.row = X.at<float>(p.rowstat0);
-    a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo);
+    a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo); a.tf32 = 1;
     CTN_TRY(launch_gemm(a, s));
   }
   for (int b = 0; b < nblk; ++b) {
@@ -314,8 +325,9 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       GemmArgs a = {};
       a.A = X.x(b); a.W = X.blk(b, L.W1); a.D = X.z1(b); a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
       a.stat_out = X.stat_out(b, 0); a.alpha_out = X.blk(b, L.a1);
-      a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * 2;
-      a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * 2;
+      a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * 4;
+      a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * 4;
+      a.tf32 = 1;
       CTN_TRY(launch_gemm(a, s));
     }
     if (!gln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
@@ -330,15 +342,16 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.c1 = X.at<float>(p.c1) + (int64_t)b * c.B; a.c2 = X.at<float>(p.c2) + (int64_t)b * c.B;
       a.st = X.stats(b, 1);
       a.res = X.x(b);
-      a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * 2;
-      a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * 2;
+      a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * 4;
+      a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * 4;
+      a.tf32 = 1;
       CTN_TRY(launch_gemm(a, s));
     }
   }
   {  // mask conv
     GemmArgs a = {};
     a.A = X.x(nblk); a.W = X.params + L.Wm; a.D = X.at<float>(p.score); a.F = F; a.O = c.C * c.N; a.Kd = c.B; a.K = K;
-    a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo);
+    a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo); a.tf32 = 1;
     CTN_TRY(launch_gemm(a, s));
   }
   return run_decoder_fwd(X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
@@ -413,12 +426,12 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       CTN_TRY(launch_wgrad(wa, s));
     }
     CTN_TRY(run_norm_bwd_reduce(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), M, K, c.H, gblk(b, L.g2),
-                                gblk(b, L.b2), gln ? X.red(b, 1) : nullptr, s));
+                                gblk(b, L.b2), gln ? X.red(b, 1) : nullptr, X.at<float>(p.part), s));
     CTN_TRY(run_norm_bwd_apply(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), M, K, c.H,
                                gblk(b, L.a2), s));
     CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K, c.H,
                            c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1),
-                           gln ? X.red(b, 0) : nullptr, s));
+                           gln ? X.red(b, 0) : nullptr, X.at<float>(p.part), s));
     CTN_TRY(run_norm_bwd_apply(dn1, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.red(b, 0), M, K, c.H,
                                gblk(b, L.a1), s));
     {  // dW1 = dz1^T x
@@ -450,7 +463,8 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     a.W_hi = X.at<char>(p.pl_WbT); a.W_lo = X.at<char>(p.pl_WbT + p.pl_lo);
     CTN_TRY(launch_gemm(a, s));
   }
-  CTN_TRY(run_norm_bwd_reduce(dn0, w, nullptr, st0, X.params + L.g0, M, K, c.N, grads + L.g0, grads + L.b0, nullptr, s));
+  CTN_TRY(run_norm_bwd_reduce(dn0, w, nullptr, st0, X.params + L.g0, M, K, c.N, grads + L.g0, grads + L.b0, nullptr,
+                              X.at<float>(p.part), s));
   CTN_TRY(run_norm_bwd_apply(dn0, w, nullptr, st0, X.params + L.g0, nullptr, M, K, c.N, nullptr, s));
   return run_encoder_bwd(mixture, w, dn0, d_w, M, p.T, c.N, c.L, grads + L.U, s);
 }
