@@ -187,7 +187,7 @@ struct TcGemmArgs {
   const float* A;  // [F, Kd] fp32
   float* D;        // [F, O]
   int64_t F;
-  int O, Kd, K, NF, stages;
+  int O, Kd, K, NF, stages, groups;
   const float* alpha_in;
   const float* c1;
   const float* c2;
@@ -232,12 +232,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   } else if (warp == 2) {
-    tmem_alloc<256>(tmem_ptr);
+    tmem_alloc<512>(tmem_ptr);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // TMEM accumulators (NF fp32 columns each).  The tensor core truncates (round-toward-zero) when it adds into its
+  // fp32 accumulator, a coherent bias that grows with the length of the accumulation chain (measured: 2.7e-6 over a
+  // 96-MMA chain vs 4e-7 for fp32 FFMA).  The TF32 (forward) flavour therefore keeps the small correction products
+  // lo*hi + hi*lo in their own accumulator (index NG) and spreads the hi*hi chain round-robin over NG accumulators;
+  // the epilogue sums them in fp32 round-to-nearest.  The bf16 (gradient) flavour uses a single accumulator.
+  const int NG = TF32 ? a.groups : 1;
 
   if (warp == 0) {
     // ===== TMA producer: weight hi/lo planes =====
@@ -267,9 +273,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           const uint64_t dwh = make_desc(w_hi + ko, 16, 1024), dwl = make_desc(w_lo + ko, 16, 1024);
           const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
           if (TF32) {
-            umma_tf32(tmem_base, dwl, dah, idesc, (kb | k) != 0);  // lo*hi
-            umma_tf32(tmem_base, dwh, dal, idesc, 1);              // hi*lo
-            umma_tf32(tmem_base, dwh, dah, idesc, 1);              // hi*hi
+            const int cstep = kb * 4 + k;
+            const uint32_t t_corr = tmem_base + (uint32_t)(NG * NF);
+            const uint32_t t_main = tmem_base + (uint32_t)((cstep % NG) * NF);
+            umma_tf32(t_corr, dwl, dah, idesc, cstep != 0);   // lo*hi  -> correction accumulator
+            umma_tf32(t_corr, dwh, dal, idesc, 1);            // hi*lo  -> correction accumulator
+            umma_tf32(t_main, dwh, dah, idesc, cstep >= NG);  // hi*hi  -> main accumulator (cstep mod NG)
           } else {
             umma_bf16(tmem_base, dwl, dah, idesc, (kb | k) != 0);
             umma_bf16(tmem_base, dwh, dal, idesc, 1);
@@ -364,6 +373,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     for (int j = jb; j < je; j += 8) {
       float acc[8];
       tmem_ld8(taddr + (uint32_t)j, acc);
+      if (TF32) {
+        for (int gidx = 1; gidx <= NG; ++gidx) {  // remaining main accumulators, then the correction accumulator
+          float more[8];
+          tmem_ld8(taddr + (uint32_t)(gidx * NF + j), more);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += more[i];
+        }
+      }
       const int nj = min(8, je - j);
       const bool uniform = !STATS || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
       if (nj == 8 && uniform) {  // fast path: whole chunk valid, one sample
@@ -424,7 +441,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<256>(tmem_base);
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -700,11 +717,12 @@ static int make_plane_map(CUtensorMap* map, const void* plane, int rows, int col
   return 0;
 }
 
-static int pick_nf(int64_t F, int o_tiles) {
-  // frames per tile (multiple of 16, <= 256) minimising (waves * tile time) on 148 SMs
+static int pick_nf(int64_t F, int o_tiles, bool tf32) {
+  // frames per tile (multiple of 16, <= 256) minimising (waves * tile time) on 148 SMs; the TF32 flavour needs room
+  // for >= 2 main accumulators + 1 correction accumulator in the 512 TMEM columns
   int best = 128;
   double best_cost = 1e30;
-  for (int nf = 64; nf <= 256; nf += 16) {
+  for (int nf = 64; nf <= (tf32 ? 160 : 256); nf += 16) {
     const int64_t tiles = (F + nf - 1) / nf * o_tiles;
     const int64_t waves = (tiles + 147) / 148;
     const double cost = (double)waves * (nf + 40);  // + fixed per-tile overhead (prologue/epilogue)
@@ -741,7 +759,9 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   CTN_TRY(make_plane_map(&ml, g.W_lo, g.O, g.Kd, tf32));
   TcGemmArgs a;
   a.A = g.A; a.D = g.D; a.F = g.F; a.O = g.O; a.Kd = g.Kd; a.K = g.K;
-  a.NF = pick_nf(g.F, g.O / BM);
+  a.NF = pick_nf(g.F, g.O / BM, tf32);
+  a.groups = 512 / a.NF - 1;
+  if (a.groups > 4) a.groups = 4;
   a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
   a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
   a.stages = tc_gemm_stages(a.NF);

