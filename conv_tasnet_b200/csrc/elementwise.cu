@@ -173,31 +173,41 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
 #pragma unroll
       for (int p = 0; p < NP_; ++p) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; ++kk) {
-      const int k = k0 + kk;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kk = 0; kk < nk; kk += 2) {
+      // all tap loads of two output frames first (ILP), then the math
+      float4 tv[2][NP_];
+      float2 stv[2][NP_];
+      bool ok[2][NP_];
 #pragma unroll
-      for (int p = 0; p < NP_; ++p) {
-        const int ks = k + (p - cshift) * dil;
-        if (p >= PP || ks < 0 || ks >= K) continue;  // zero padding is applied after the norm
-        float mu, r;
-        if (st1.row != nullptr) {
-          const float2 v = reinterpret_cast<const float2*>(st1.row)[base + ks];
-          mu = v.x; r = v.y;
-        } else {
-          mu = s_st.x; r = s_st.y;
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int p = 0; p < NP_; ++p) {
+          const int ks = k0 + kk + u + (p - cshift) * dil;
+          ok[u][p] = p < PP && kk + u < nk && ks >= 0 && ks < K;  // zero padding is applied after the norm
+          tv[u][p] = ok[u][p] ? ld4(z1 + (base + ks) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          stv[u][p] = (ok[u][p] && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + ks] : s_st;
         }
-        float4 v = prelu4(ld4(z1 + (base + ks) * H + c), a1);
-        o.x = fmaf(wd[0][p], g.x * (v.x - mu) * r + b.x, o.x);
-        o.y = fmaf(wd[1][p], g.y * (v.y - mu) * r + b.y, o.y);
-        o.z = fmaf(wd[2][p], g.z * (v.z - mu) * r + b.z, o.z);
-        o.w = fmaf(wd[3][p], g.w * (v.w - mu) * r + b.w, o.w);
       }
-      st4(z2 + (base + k) * H + c, o);
-      if (do_stats) {
-        const float4 q = prelu4(o, a2);
-        s += (q.x + q.y) + (q.z + q.w);
-        s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (kk + u >= nk) break;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < NP_; ++p) {
+          if (!ok[u][p]) continue;
+          const float mu = stv[u][p].x, r = stv[u][p].y;
+          const float4 v = prelu4(tv[u][p], a1);
+          o.x = fmaf(wd[0][p], g.x * (v.x - mu) * r + b.x, o.x);
+          o.y = fmaf(wd[1][p], g.y * (v.y - mu) * r + b.y, o.y);
+          o.z = fmaf(wd[2][p], g.z * (v.z - mu) * r + b.z, o.z);
+          o.w = fmaf(wd[3][p], g.w * (v.w - mu) * r + b.w, o.w);
+        }
+        st4(z2 + (base + k0 + kk + u) * H + c, o);
+        if (do_stats) {
+          const float4 q = prelu4(o, a2);
+          s += (q.x + q.y) + (q.z + q.w);
+          s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+        }
       }
     }
     acc[0] += (double)s;

@@ -117,6 +117,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -372,14 +379,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     int cur_m = STATS && jb < je ? s_m[jb] : -1;
     for (int j = jb; j < je; j += 8) {
       float acc[8];
-      tmem_ld8(taddr + (uint32_t)j, acc);
-      if (TF32) {
-        for (int gidx = 1; gidx <= NG; ++gidx) {  // remaining main accumulators, then the correction accumulator
-          float more[8];
-          tmem_ld8(taddr + (uint32_t)(gidx * NF + j), more);
+      if (TF32) {  // all accumulators of this chunk in flight, one wait, then fp32 round-to-nearest sums
+        uint32_t raw[5][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += more[i];
-        }
+        for (int gidx = 0; gidx < 5; ++gidx)
+          if (gidx <= NG) tmem_ld8_issue(taddr + (uint32_t)(gidx * NF + j), raw[gidx]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[0][i]);
+#pragma unroll
+        for (int gidx = 1; gidx < 5; ++gidx)
+          if (gidx <= NG) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(raw[gidx][i]);
+          }
+      } else {
+        tmem_ld8(taddr + (uint32_t)j, acc);
       }
       const int nj = min(8, je - j);
       const bool uniform = !STATS || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
