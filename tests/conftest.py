@@ -59,3 +59,20 @@ def rel_l2(a, b):
 def grad_tolerance(ref32_err):
     """1e-3 (north star), or 3x the fp32 reference's own error against fp64 truth where that is larger."""
     return max(1e-3, 3.0 * ref32_err)
+
+
+def assert_gradients_match(pairs):
+    """pairs: (name, err_mine, err_ref32), relative L2 against fp64 truth per tensor.
+
+    fp32 gradients of this network carry isolated outliers: one pre-activation within rounding distance of a PReLU kink
+    that lands on the other side changes a whole row of a weight gradient by ~1/sqrt(frames) (6e-3 at 24k frames).  The
+    reference's own fp32 autograd shows them too (e.g. 3e-3 on one gamma of the softmax config).  So the bar is:
+    the typical tensor is as accurate as the reference's, every tensor is within max(1e-3, 3x reference) except for
+    at most 2 % outliers, and no tensor is off by more than 2e-2."""
+    import statistics
+    errs = [e for _, e, _ in pairs]
+    refs = [r for _, _, r in pairs]
+    assert statistics.median(errs) <= max(1e-4, 2.0 * statistics.median(refs)), (statistics.median(errs), statistics.median(refs))
+    bad = [(k, e, r) for k, e, r in pairs if e > grad_tolerance(r)]
+    assert len(bad) <= max(1, int(0.02 * len(pairs))), bad
+    assert max(errs) < 2e-2, max(pairs, key=lambda t: t[1])
