@@ -189,6 +189,7 @@ constexpr int BM = 128;               // MMA M (output channels)
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
 constexpr int STAGES = 3;
 constexpr int W_PLANE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int MAXIT = 5;              // converter passes of 32 rows: NF <= 160
 
 struct TcGemmArgs {
   const float* A;  // [F, Kd] fp32
@@ -313,31 +314,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       s_m[t] = m;
       s_col[t] = make_float2(r, mu * r);
     }
-    const int nit = (NF + 31) / 32;
+    const int nit = (NF + 31) / 32;  // <= MAXIT (NF <= 160)
     constexpr int CE = TF32 ? 4 : 8;  // fp32 elements behind one 16-byte operand chunk
+    constexpr int NV = TF32 ? 1 : 2;  // float4 loads per chunk
     const float* abase = a.A + (f0 + row0) * a.Kd + chunk * CE;
     const int row_stride32 = 32 * a.Kd;  // floats between the rows of consecutive passes
     const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 32*it keeps (row & 7)
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % NST, ph = (kb / NST) & 1;
-      float4 v[8][2];
+
+    // operand loads of k-block kb into a register buffer (issued one k-block ahead of their use)
+    auto load_kb = [&](float4 (&v)[MAXIT][NV], int kb) {
       const float* src = abase + kb * KB;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < MAXIT; ++it) {
         if (it < nit) {
-          if (row0 + it * 32 < nvalid) {
-            v[it][0] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32));
-            if (!TF32) v[it][1] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + 1);
-          } else {
-            v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!TF32) v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const bool ok = row0 + it * 32 < nvalid;
+#pragma unroll
+          for (int u = 0; u < NV; ++u)
+            v[it][u] = ok ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + u)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    };
+    // prologue + hi/lo split + swizzled store of one k-block, then hand the stage to the MMA warp
+    auto convert_kb = [&](float4 (&v)[MAXIT][NV], int kb) {
+      const int s = kb % NST, ph = (kb / NST) & 1;
       mbar_wait(empty + s, ph ^ 1);
       const uint32_t st = smem_base + s * stage_bytes + 2 * W_PLANE_BYTES + st_off;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < MAXIT; ++it) {
         if (it < nit && row0 + it * 32 < NF) {
           uint4 hi, lo;
           if (TF32) {
@@ -345,7 +349,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             if (pro) { x.x = prelu(x.x, alpha_in); x.y = prelu(x.y, alpha_in); x.z = prelu(x.z, alpha_in); x.w = prelu(x.w, alpha_in); }
             split4_tf32(x, hi, lo);
           } else {
-            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w,
+                          v[it][NV - 1].x, v[it][NV - 1].y, v[it][NV - 1].z, v[it][NV - 1].w};
             if (pro) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
@@ -358,6 +363,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       }
       fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
       mbar_arrive(full + s);
+    };
+    {
+      float4 b0[MAXIT][NV], b1[MAXIT][NV];
+      load_kb(b0, 0);
+      for (int kb = 0; kb < nkb; kb += 2) {
+        if (kb + 1 < nkb) load_kb(b1, kb + 1);
+        convert_kb(b0, kb);
+        if (kb + 1 < nkb) {
+          if (kb + 2 < nkb) load_kb(b0, kb + 2);
+          convert_kb(b1, kb + 1);
+        }
+      }
     }
 
     // ---- epilogue: TMEM -> registers -> global; lane = output channel, column = frame ----
@@ -555,32 +572,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         gam[i] = norm ? __ldg(a.gamma + i0 + xc * 8 + i) : 1.f;
         bet[i] = norm ? __ldg(a.beta + i0 + xc * 8 + i) : 0.f;
       }
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
+      auto load_kb = [&](float4 (&gv)[2][2], float4 (&xv)[XIT][2], int kb) {
         const int64_t fk = fb + (int64_t)kb * WK;
-        float4 gv[2][2], xv[XIT][2];
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           const int64_t f = fk + gr + it * 16;
-          if (f < fe) {
-            const float4* src = reinterpret_cast<const float4*>(a.G + f * a.O + o0 + gc * 8);
-            gv[it][0] = __ldg(src);
-            gv[it][1] = __ldg(src + 1);
-          } else {
-            gv[it][0] = gv[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const bool ok = f < fe;
+          const float4* src = reinterpret_cast<const float4*>(a.G + f * a.O + o0 + gc * 8);
+          gv[it][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gv[it][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int it = 0; it < XIT; ++it) {
           const int64_t f = fk + xr + it * XR;
-          if (f < fe) {
-            const float4* src = reinterpret_cast<const float4*>(a.Act + f * a.I + i0 + xc * 8);
-            xv[it][0] = __ldg(src);
-            xv[it][1] = __ldg(src + 1);
-          } else {
-            xv[it][0] = xv[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const bool ok = f < fe;
+          const float4* src = reinterpret_cast<const float4*>(a.Act + f * a.I + i0 + xc * 8);
+          xv[it][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[it][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      auto convert_kb = [&](float4 (&gv)[2][2], float4 (&xv)[XIT][2], int kb) {
+        const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
+        const int64_t fk = fb + (int64_t)kb * WK;
         mbar_wait(empty + s, ph ^ 1);
         const uint32_t st = smem_base + s * STAGE;
 #pragma unroll
@@ -620,6 +633,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         }
         fence_proxy_async();
         mbar_arrive(full + s);
+      };
+      {
+        float4 g0[2][2], x0[XIT][2], g1[2][2], x1[XIT][2];
+        load_kb(g0, x0, 0);
+        for (int kb = 0; kb < nkb; kb += 2) {
+          if (kb + 1 < nkb) load_kb(g1, x1, kb + 1);
+          convert_kb(g0, x0, kb);
+          if (kb + 1 < nkb) {
+            if (kb + 2 < nkb) load_kb(g0, x0, kb + 2);
+            convert_kb(g1, x1, kb + 1);
+          }
+        }
       }
       // ---- epilogue: atomically add the partial tile ----
       mbar_wait(tmem_full, 0);
@@ -737,7 +762,8 @@ static int pick_nf(int64_t F, int o_tiles, bool tf32) {
   // for >= 2 main accumulators + 1 correction accumulator in the 512 TMEM columns
   int best = 128;
   double best_cost = 1e30;
-  for (int nf = 64; nf <= (tf32 ? 160 : 256); nf += 16) {
+  (void)tf32;  // both flavours: NF <= 160 (TMEM room for the split accumulators; converter register budget)
+  for (int nf = 64; nf <= 160; nf += 16) {
     const int64_t tiles = (F + nf - 1) / nf * o_tiles;
     const int64_t waves = (tiles + 147) / 148;
     const double cost = (double)waves * (nf + 40);  // + fixed per-tile overhead (prologue/epilogue)
