@@ -26,6 +26,12 @@
 #include "common.cuh"
 
 namespace ctn {
+#ifdef CTN_TRACE
+__device__ long long g_trace[512][64];
+#define TR(slot) do { g_trace[blockIdx.y * gridDim.x + blockIdx.x][slot] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -101,6 +107,43 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The same MMAs with the shared-memory descriptors passed as (low word, shared high word): the high word (SBO, version,
+// swizzle mode) never changes and the low word is (addr >> 4) | (LBO >> 4) << 16, so stepping along K is one IADD.
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrives when every MMA issued so far by this thread has finished (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -189,7 +232,7 @@ constexpr int BM = 128;               // MMA M (output channels)
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
 constexpr int STAGES = 3;
 constexpr int W_PLANE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int MAXIT = 5;              // converter passes of 32 rows: NF <= 160
+constexpr int MAXIT = 10;             // converter passes of 16 rows per group: NF <= 160
 
 struct TcGemmArgs {
   const float* A;  // [F, Kd] fp32
@@ -226,6 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   int* s_m = reinterpret_cast<int*>(s_col + 256);           // [256] sample index
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TR(0);
   const int64_t f0 = (int64_t)blockIdx.x * NF;
   const int o0 = blockIdx.y * BM;
   constexpr int KB = TF32 ? 32 : 64;  // elements per 128-byte swizzle row = K extent of one stage
@@ -234,7 +278,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full + s, 1 + CONV_THREADS);
+      mbar_init(full + s, 1 + CONV_THREADS / 2);  // TMA producer + one converter group
       mbar_init(empty + s, 1);
     }
     mbar_init(tmem_full, 1);
@@ -246,6 +290,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) TR(1);
   // TMEM accumulators (NF fp32 columns each).  The tensor core truncates (round-toward-zero) when it adds into its
   // fp32 accumulator, a coherent bias that grows with the length of the accumulation chain (measured: 2.7e-6 over a
   // 96-MMA chain vs 4e-7 for fp32 FFMA).  The TF32 (forward) flavour therefore keeps the small correction products
@@ -269,80 +314,73 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, NF, 0, 0, TF32 ? 2u : 1u);
+      const uint32_t dhi = desc_hi_sw128(1024);
+      const uint32_t t_corr = tmem_base + (uint32_t)(NG * NF);
+      int cstep = 0, gsel = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST, ph = (kb / NST) & 1;
         mbar_wait(full + s, ph);
         tc_fence_after();
+        if (kb < 16) TR(8 + kb);
         const uint32_t sb = smem_base + s * stage_bytes;
-        const uint32_t w_hi = sb, w_lo = sb + W_PLANE_BYTES, a_hi = sb + 2 * W_PLANE_BYTES, a_lo = a_hi + a_plane;
+        uint32_t w_hi = desc_lo(sb, 16), w_lo = desc_lo(sb + W_PLANE_BYTES, 16);
+        uint32_t a_hi = desc_lo(sb + 2 * W_PLANE_BYTES, 16), a_lo = desc_lo(sb + 2 * W_PLANE_BYTES + a_plane, 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t ko = k * 32;  // one MMA consumes 32 bytes of K per row (16 bf16 or 8 tf32)
-          const uint64_t dwh = make_desc(w_hi + ko, 16, 1024), dwl = make_desc(w_lo + ko, 16, 1024);
-          const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+        for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row (16 bf16 or 8 tf32): +2 in the descriptor
           if (TF32) {
-            const int cstep = kb * 4 + k;
-            const uint32_t t_corr = tmem_base + (uint32_t)(NG * NF);
-            const uint32_t t_main = tmem_base + (uint32_t)((cstep % NG) * NF);
-            umma_tf32(t_corr, dwl, dah, idesc, cstep != 0);   // lo*hi  -> correction accumulator
-            umma_tf32(t_corr, dwh, dal, idesc, 1);            // hi*lo  -> correction accumulator
-            umma_tf32(t_main, dwh, dah, idesc, cstep >= NG);  // hi*hi  -> main accumulator (cstep mod NG)
+            umma_lo<true>(t_corr, w_lo, a_hi, dhi, idesc, cstep != 0);                         // lo*hi -> correction
+            umma_lo<true>(t_corr, w_hi, a_lo, dhi, idesc, 1);                                  // hi*lo -> correction
+            umma_lo<true>(tmem_base + (uint32_t)(gsel * NF), w_hi, a_hi, dhi, idesc, cstep >= NG);  // hi*hi -> main[gsel]
+            gsel = gsel + 1 == NG ? 0 : gsel + 1;
           } else {
-            umma_bf16(tmem_base, dwl, dah, idesc, (kb | k) != 0);
-            umma_bf16(tmem_base, dwh, dal, idesc, 1);
-            umma_bf16(tmem_base, dwh, dah, idesc, 1);
+            umma_lo<false>(tmem_base, w_lo, a_hi, dhi, idesc, cstep != 0);
+            umma_lo<false>(tmem_base, w_hi, a_lo, dhi, idesc, 1);
+            umma_lo<false>(tmem_base, w_hi, a_hi, dhi, idesc, 1);
           }
+          ++cstep;
+          w_hi += 2; w_lo += 2; a_hi += 2; a_lo += 2;
         }
         umma_commit(empty + s);  // frees the stage when these MMAs have read it
       }
       umma_commit(tmem_full);
+      TR(2);
     }
   } else if (warp >= 4) {
     // ===== converters (fp32 -> bf16 hi/lo, swizzled K-major) then epilogue =====
     const int t = threadIdx.x - 128;  // 0..255
-    const int chunk = t & 7, row0 = t >> 3;
     const bool pro = a.alpha_in != nullptr;
     const float alpha_in = pro ? __ldg(a.alpha_in) : 1.f;
     const int nvalid = (int)(a.F - f0 < NF ? a.F - f0 : NF);  // frames of this tile that exist
-    if (t < NF) {  // per-column (frame) metadata for the epilogue
-      int m = -1;
-      float mu = 0.f, r = 1.f;
-      if (t < nvalid) {
-        m = (int)((f0 + t) / a.K);
-        if (FOLD) load_stats(a.st, m, f0 + t, mu, r);
-      }
-      s_m[t] = m;
-      s_col[t] = make_float2(r, mu * r);
-    }
-    const int nit = (NF + 31) / 32;  // <= MAXIT (NF <= 160)
-    constexpr int CE = TF32 ? 4 : 8;  // fp32 elements behind one 16-byte operand chunk
-    constexpr int NV = TF32 ? 1 : 2;  // float4 loads per chunk
-    const float* abase = a.A + (f0 + row0) * a.Kd + chunk * CE;
-    const int row_stride32 = 32 * a.Kd;  // floats between the rows of consecutive passes
-    const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 32*it keeps (row & 7)
-
-    // operand loads of k-block kb into a register buffer (issued one k-block ahead of their use)
-    auto load_kb = [&](float4 (&v)[MAXIT][NV], int kb) {
-      const float* src = abase + kb * KB;
+    // Two groups of 4 warps alternate k-blocks: while one group waits for its global loads, the other converts and
+    // publishes its stage.  (The per-thread fence.proxy.async drains that thread's outstanding loads, so prefetching
+    // inside one thread does not overlap anything; alternating groups does.)
+    const int grp = t >> 7, tg = t & 127;
+    const int chunk = tg & 7, row0 = tg >> 3;     // 16 rows per pass
+    const int nit = (NF + 15) / 16;               // <= MAXIT
+    constexpr int CE = TF32 ? 4 : 8;              // fp32 elements behind one 16-byte operand chunk
+    constexpr int NV = TF32 ? 1 : 2;              // float4 loads per chunk
+    const float4* abase = reinterpret_cast<const float4*>(a.A + (f0 + row0) * a.Kd + chunk * CE);
+    const int row_stride16 = 4 * a.Kd;            // float4s between the rows of consecutive passes (16 rows)
+    const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 16*it keeps (row & 7)
+    for (int kb = grp; kb < nkb; kb += 2) {
+      const int s = kb % NST, ph = (kb / NST) & 1;
+      float4 v[MAXIT][NV];
+      const float4* src = abase + kb * (KB / 4);
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
         if (it < nit) {
-          const bool ok = row0 + it * 32 < nvalid;
+          const bool ok = row0 + it * 16 < nvalid;
 #pragma unroll
           for (int u = 0; u < NV; ++u)
-            v[it][u] = ok ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)it * row_stride32) + u)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[it][u] = ok ? __ldg(src + it * row_stride16 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-    };
-    // prologue + hi/lo split + swizzled store of one k-block, then hand the stage to the MMA warp
-    auto convert_kb = [&](float4 (&v)[MAXIT][NV], int kb) {
-      const int s = kb % NST, ph = (kb / NST) & 1;
+      if (tg == 0 && kb < 16) TR(24 + kb);   // loads issued
       mbar_wait(empty + s, ph ^ 1);
       const uint32_t st = smem_base + s * stage_bytes + 2 * W_PLANE_BYTES + st_off;
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
-        if (it < nit && row0 + it * 32 < NF) {
+        if (it < nit && row0 + it * 16 < NF) {
           uint4 hi, lo;
           if (TF32) {
             float4 x = v[it][0];
@@ -357,30 +395,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             }
             split8(x, hi, lo);
           }
-          sts128(st + it * 32 * 128, hi);
-          sts128(st + it * 32 * 128 + a_plane, lo);
+          sts128(st + it * 16 * 128, hi);
+          sts128(st + it * 16 * 128 + a_plane, lo);
         }
       }
       fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
       mbar_arrive(full + s);
-    };
-    {
-      float4 b0[MAXIT][NV], b1[MAXIT][NV];
-      load_kb(b0, 0);
-      for (int kb = 0; kb < nkb; kb += 2) {
-        if (kb + 1 < nkb) load_kb(b1, kb + 1);
-        convert_kb(b0, kb);
-        if (kb + 1 < nkb) {
-          if (kb + 2 < nkb) load_kb(b0, kb + 2);
-          convert_kb(b1, kb + 1);
-        }
-      }
+      if (tg == 0 && kb < 16) TR(40 + kb);   // stage published
     }
 
     // ---- epilogue: TMEM -> registers -> global; lane = output channel, column = frame ----
+    if (t < NF) {  // per-column (frame) metadata (sample index, norm-fold scalars), off the mainloop's critical path
+      int m = -1;
+      float mu = 0.f, r = 1.f;
+      if (t < nvalid) {
+        m = (int)((uint32_t)(f0 + t) / (uint32_t)a.K);
+        if (FOLD) load_stats(a.st, m, f0 + t, mu, r);
+      }
+      s_m[t] = m;
+      s_col[t] = make_float2(r, mu * r);
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");  // column metadata written by the converter threads
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (t == 0) TR(3);
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int o = o0 + q * 32 + lane;
     const int O = a.O;
@@ -394,25 +432,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
     int cur_m = STATS && jb < je ? s_m[jb] : -1;
-    for (int j = jb; j < je; j += 8) {
+    constexpr int NACC = TF32 ? 5 : 1;  // TMEM tiles summed per output (NG main + 1 correction, NG <= 4)
+    uint32_t rawA[NACC][8], rawB[NACC][8];
+    auto issue = [&](uint32_t (&dst)[NACC][8], int j) {
+#pragma unroll
+      for (int gidx = 0; gidx < NACC; ++gidx)
+        if (gidx <= (TF32 ? NG : 0)) tmem_ld8_issue(taddr + (uint32_t)(gidx * NF + j), dst[gidx]);
+    };
+    auto process = [&](uint32_t (&cur)[NACC][8], int j) {
       float acc[8];
-      if (TF32) {  // all accumulators of this chunk in flight, one wait, then fp32 round-to-nearest sums
-        uint32_t raw[5][8];
 #pragma unroll
-        for (int gidx = 0; gidx < 5; ++gidx)
-          if (gidx <= NG) tmem_ld8_issue(taddr + (uint32_t)(gidx * NF + j), raw[gidx]);
-        tmem_ld_wait();
+      for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(cur[0][i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[0][i]);
+      for (int gidx = 1; gidx < NACC; ++gidx)
+        if (gidx <= (TF32 ? NG : 0)) {
 #pragma unroll
-        for (int gidx = 1; gidx < 5; ++gidx)
-          if (gidx <= NG) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(raw[gidx][i]);
-          }
-      } else {
-        tmem_ld8(taddr + (uint32_t)j, acc);
-      }
+          for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(cur[gidx][i]);
+        }
       const int nj = min(8, je - j);
       const bool uniform = !STATS || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
       if (nj == 8 && uniform) {  // fast path: whole chunk valid, one sample
@@ -462,6 +498,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           }
         }
       }
+    };
+    // software pipeline: the TMEM loads of the next 8 columns are in flight while this chunk is processed
+    if (jb < je) issue(rawA, jb);
+    for (int j = jb; j < je; j += 16) {
+      tmem_ld_wait();
+      if (j + 8 < je) issue(rawB, j + 8);
+      process(rawA, j);
+      if (j + 8 < je) {
+        tmem_ld_wait();
+        if (j + 16 < je) issue(rawA, j + 16);
+        process(rawB, j + 8);
+      }
     }
     if (STATS && cur_m >= 0) {
       const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
@@ -471,9 +519,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       }
     }
   }
+  if (threadIdx.x == 128) TR(4);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (threadIdx.x == 0) TR(5);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -519,7 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();
     for (int s = 0; s < WSTAGES; ++s) {
-      mbar_init(full + s, CONV_THREADS);
+      mbar_init(full + s, CONV_THREADS / 2);  // one converter group per k-block
       mbar_init(empty + s, 1);
     }
     mbar_init(tmem_full, 1);
@@ -557,26 +607,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
       }
     } else if (warp >= 4) {
       const int t = threadIdx.x - 128;
+      const int grp = t >> 7, tg = t & 127;  // two groups of 4 warps alternate k-blocks (see tc_gemm_kernel)
       const bool norm = a.gamma != nullptr, hasp = a.alpha != nullptr;
       const float alpha = hasp ? __ldg(a.alpha) : 1.f;
-      // G tile: 32 rows x 16 chunks (8 floats each): 2 chunks per thread (rows t/16 and t/16 + 16)
-      const int gc = t & 15, gr = t >> 4;
+      // G tile: 32 rows x 16 chunks (8 floats each): 4 chunks per thread (rows tg/16 + 8*it)
+      const int gc = tg & 15, gr = tg >> 4;
       // Act tile: 32 rows x NI/8 chunks
-      constexpr int XC = NI / 8;              // chunks per row
-      constexpr int XR = CONV_THREADS / XC;   // rows covered per pass
+      constexpr int XC = NI / 8;        // chunks per row
+      constexpr int XR = 128 / XC;      // rows covered per pass
       constexpr int XIT = WK / XR;
-      const int xc = t % XC, xr = t / XC;
+      const int xc = tg % XC, xr = tg / XC;
       float gam[8], bet[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         gam[i] = norm ? __ldg(a.gamma + i0 + xc * 8 + i) : 1.f;
         bet[i] = norm ? __ldg(a.beta + i0 + xc * 8 + i) : 0.f;
       }
-      auto load_kb = [&](float4 (&gv)[2][2], float4 (&xv)[XIT][2], int kb) {
+      for (int kb = grp; kb < nkb; kb += 2) {
+        const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
         const int64_t fk = fb + (int64_t)kb * WK;
+        float4 gv[4][2], xv[XIT][2];
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int64_t f = fk + gr + it * 16;
+        for (int it = 0; it < 4; ++it) {
+          const int64_t f = fk + gr + it * 8;
           const bool ok = f < fe;
           const float4* src = reinterpret_cast<const float4*>(a.G + f * a.O + o0 + gc * 8);
           gv[it][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -590,15 +643,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           xv[it][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
           xv[it][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      };
-      auto convert_kb = [&](float4 (&gv)[2][2], float4 (&xv)[XIT][2], int kb) {
-        const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
-        const int64_t fk = fb + (int64_t)kb * WK;
         mbar_wait(empty + s, ph ^ 1);
         const uint32_t st = smem_base + s * STAGE;
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int k = gr + it * 16;
+        for (int it = 0; it < 4; ++it) {
+          const int k = gr + it * 8;
           const float x[8] = {gv[it][0].x, gv[it][0].y, gv[it][0].z, gv[it][0].w,
                               gv[it][1].x, gv[it][1].y, gv[it][1].z, gv[it][1].w};
           uint4 hi, lo;
@@ -633,18 +682,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         }
         fence_proxy_async();
         mbar_arrive(full + s);
-      };
-      {
-        float4 g0[2][2], x0[XIT][2], g1[2][2], x1[XIT][2];
-        load_kb(g0, x0, 0);
-        for (int kb = 0; kb < nkb; kb += 2) {
-          if (kb + 1 < nkb) load_kb(g1, x1, kb + 1);
-          convert_kb(g0, x0, kb);
-          if (kb + 1 < nkb) {
-            if (kb + 2 < nkb) load_kb(g0, x0, kb + 2);
-            convert_kb(g1, x1, kb + 1);
-          }
-        }
       }
       // ---- epilogue: atomically add the partial tile ----
       mbar_wait(tmem_full, 0);
@@ -884,3 +921,9 @@ int run_split_planes(const float* src, int R, int C, int nb, int64_t src_stride,
 }
 
 }  // namespace ctn
+
+#ifdef CTN_TRACE
+extern "C" int ctn_debug_read_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, ctn::g_trace, sizeof(long long) * 64 * n);
+}
+#endif
