@@ -217,6 +217,11 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float2 lds64(uint32_t saddr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
@@ -230,15 +235,15 @@ constexpr int TC_THREADS = 384;       // 4 control warps + 8 converter/epilogue 
 constexpr int CONV_THREADS = 256;
 constexpr int BM = 128;               // MMA M (output channels)
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;             // operand stages (hi/lo planes of W and A)
 constexpr int W_PLANE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int MAXIT = 10;             // converter passes of 16 rows per group: NF <= 160
+constexpr int RAW_STAGES = 4;          // ring of raw fp32 activation tiles (TMA destination)
 
 struct TcGemmArgs {
   const float* A;  // [F, Kd] fp32
   float* D;        // [F, O]
   int64_t F;
-  int O, Kd, K, NF, stages, groups;
+  int O, Kd, K, NF, stages, raw_stages, groups;
   const float* alpha_in;
   const float* c1;
   const float* c2;
@@ -251,19 +256,28 @@ struct TcGemmArgs {
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad GEMM
 // ------------------------------------------------------------------------------------------------
-// smem map (dynamic, 1024-byte aligned): NST stages of [W_hi 16K | W_lo 16K | A_hi NF*128 | A_lo NF*128], then
-// barriers, the TMEM base address, and per-column epilogue metadata float2 (r, mu*r) + int sample index.
+// smem map (dynamic, 1024-byte aligned): OST operand stages of [W_hi 16K | W_lo 16K | A_hi NF*128 | A_lo NF*128], a ring
+// of RST raw fp32 activation tiles (TMA destination), then barriers, the TMEM base address, and per-column epilogue
+// metadata float2 (r, mu*r) + int sample index.
+// Warp roles: 0 = TMA producer of the weight planes, 3 = TMA producer of the raw activation tiles, 1 = MMA issuer,
+// 2 = TMEM allocator, 4..11 = converters (smem raw fp32 -> prologue -> hi/lo split -> swizzled operand planes; no global
+// loads, so nothing is in flight when they fence) and afterwards the epilogue.
 template <bool TF32, bool FOLD, bool RES, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcGemmArgs a) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               const __grid_constant__ CUtensorMap map_a, TcGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int NF = a.NF, NST = a.stages;
+  const int NF = a.NF, NST = a.stages, RST = a.raw_stages;
   const int a_plane = NF * 128;
   const int stage_bytes = 2 * W_PLANE_BYTES + 2 * a_plane;
+  const int raw_bytes = a_plane * (TF32 ? 1 : 2);  // one 32-float box per row (TF32) or two (bf16: 64 K-elements)
   const uint32_t smem_base = smem_u32(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * stage_bytes);
+  const uint32_t raw_base = smem_base + NST * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * stage_bytes + RST * raw_bytes);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* raw_full = empty + STAGES;
+  uint64_t* raw_empty = raw_full + RAW_STAGES;
+  uint64_t* tmem_full = raw_empty + RAW_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float2* s_col = reinterpret_cast<float2*>(tmem_ptr + 2);  // [256] (r, mu*r)
   int* s_m = reinterpret_cast<int*>(s_col + 256);           // [256] sample index
@@ -278,8 +292,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full + s, 1 + CONV_THREADS / 2);  // TMA producer + one converter group
+      mbar_init(full + s, 1 + CONV_THREADS);  // weight TMA producer + every converter thread
       mbar_init(empty + s, 1);
+    }
+    for (int r = 0; r < RST; ++r) {
+      mbar_init(raw_full + r, 1);
+      mbar_init(raw_empty + r, CONV_THREADS);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -299,7 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int NG = TF32 ? a.groups : 1;
 
   if (warp == 0) {
-    // ===== TMA producer: weight hi/lo planes =====
+    // ===== TMA producer: weight hi/lo planes into the operand stages =====
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST, ph = (kb / NST) & 1;
@@ -308,6 +326,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         mbar_expect_tx(full + s, 2 * W_PLANE_BYTES);
         tma_load_2d(st, &map_hi, full + s, kb * KB, o0);
         tma_load_2d(st + W_PLANE_BYTES, &map_lo, full + s, kb * KB, o0);
+      }
+    }
+  } else if (warp == 3) {
+    // ===== TMA producer: raw fp32 activation tiles [NF frames x 32 floats], rows past F are zero-filled =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int r = kb % RST, ph = (kb / RST) & 1;
+        mbar_wait(raw_empty + r, ph ^ 1);
+        uint8_t* dst = smem + NST * stage_bytes + r * raw_bytes;
+        mbar_expect_tx(raw_full + r, raw_bytes);
+        tma_load_2d(dst, &map_a, raw_full + r, kb * KB, (int)f0);
+        if (!TF32) tma_load_2d(dst + a_plane, &map_a, raw_full + r, kb * KB + 32, (int)f0);
       }
     }
   } else if (warp == 1) {
@@ -346,62 +376,82 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       TR(2);
     }
   } else if (warp >= 4) {
-    // ===== converters (fp32 -> bf16 hi/lo, swizzled K-major) then epilogue =====
+    // ===== converters: raw smem tile -> prologue -> hi/lo split -> operand planes; then the epilogue =====
     const int t = threadIdx.x - 128;  // 0..255
     const bool pro = a.alpha_in != nullptr;
     const float alpha_in = pro ? __ldg(a.alpha_in) : 1.f;
     const int nvalid = (int)(a.F - f0 < NF ? a.F - f0 : NF);  // frames of this tile that exist
-    // Two groups of 4 warps alternate k-blocks: while one group waits for its global loads, the other converts and
-    // publishes its stage.  (The per-thread fence.proxy.async drains that thread's outstanding loads, so prefetching
-    // inside one thread does not overlap anything; alternating groups does.)
-    const int grp = t >> 7, tg = t & 127;
-    const int chunk = tg & 7, row0 = tg >> 3;     // 16 rows per pass
-    const int nit = (NF + 15) / 16;               // <= MAXIT
-    constexpr int CE = TF32 ? 4 : 8;              // fp32 elements behind one 16-byte operand chunk
-    constexpr int NV = TF32 ? 1 : 2;              // float4 loads per chunk
-    const float4* abase = reinterpret_cast<const float4*>(a.A + (f0 + row0) * a.Kd + chunk * CE);
-    const int row_stride16 = 4 * a.Kd;            // float4s between the rows of consecutive passes (16 rows)
-    const uint32_t st_off = row0 * 128 + ((chunk ^ (row0 & 7)) << 4);  // row0 + 16*it keeps (row & 7)
-    for (int kb = grp; kb < nkb; kb += 2) {
+    const int nchunks = NF * 8;                 // 16-byte operand chunks per plane
+    for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % NST, ph = (kb / NST) & 1;
-      float4 v[MAXIT][NV];
-      const float4* src = abase + kb * (KB / 4);
+      const int r = kb % RST, rph = (kb / RST) & 1;
+      const uint32_t raw = raw_base + r * raw_bytes;
+      const uint32_t dst = smem_base + s * stage_bytes + 2 * W_PLANE_BYTES;
+      mbar_wait(raw_full + r, rph);       // TMA has landed the raw tile
+      if (t == 0 && kb < 16) TR(24 + kb);
+      mbar_wait(empty + s, ph ^ 1);       // the MMAs that read this operand stage have finished
+      if (TF32) {
+        // same element size in and out: the swizzled position of a 16-byte chunk is identical in the raw tile and
+        // in the operand planes, so the conversion is position-agnostic
+        // batches of 5 chunks per thread: all shared loads first (ILP), then convert + store
+        for (int q0 = t; q0 < nchunks; q0 += 5 * CONV_THREADS) {
+          float4 x[5];
 #pragma unroll
-      for (int it = 0; it < MAXIT; ++it) {
-        if (it < nit) {
-          const bool ok = row0 + it * 16 < nvalid;
-#pragma unroll
-          for (int u = 0; u < NV; ++u)
-            v[it][u] = ok ? __ldg(src + it * row_stride16 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (tg == 0 && kb < 16) TR(24 + kb);   // loads issued
-      mbar_wait(empty + s, ph ^ 1);
-      const uint32_t st = smem_base + s * stage_bytes + 2 * W_PLANE_BYTES + st_off;
-#pragma unroll
-      for (int it = 0; it < MAXIT; ++it) {
-        if (it < nit && row0 + it * 16 < NF) {
-          uint4 hi, lo;
-          if (TF32) {
-            float4 x = v[it][0];
-            if (pro) { x.x = prelu(x.x, alpha_in); x.y = prelu(x.y, alpha_in); x.z = prelu(x.z, alpha_in); x.w = prelu(x.w, alpha_in); }
-            split4_tf32(x, hi, lo);
-          } else {
-            float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w,
-                          v[it][NV - 1].x, v[it][NV - 1].y, v[it][NV - 1].z, v[it][NV - 1].w};
-            if (pro) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
-            }
-            split8(x, hi, lo);
+          for (int u = 0; u < 5; ++u) {
+            const int q = q0 + u * CONV_THREADS;
+            if (q < nchunks) x[u] = lds128f(raw + q * 16);
           }
-          sts128(st + it * 16 * 128, hi);
-          sts128(st + it * 16 * 128 + a_plane, lo);
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int q = q0 + u * CONV_THREADS;
+            if (q < nchunks) {
+              float4 y = x[u];
+              if (pro) { y.x = prelu(y.x, alpha_in); y.y = prelu(y.y, alpha_in); y.z = prelu(y.z, alpha_in); y.w = prelu(y.w, alpha_in); }
+              uint4 hi, lo;
+              split4_tf32(y, hi, lo);
+              sts128(dst + q * 16, hi);
+              sts128(dst + a_plane + q * 16, lo);
+            }
+          }
+        }
+      } else {
+        // bf16 chunk oc of row `row` = K elements [8 oc, 8 oc + 8) = raw box (oc >> 2), raw chunks 2 (oc & 3), +1
+        for (int q0 = t; q0 < nchunks; q0 += 5 * CONV_THREADS) {
+          float4 x0[5], x1[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int q = q0 + u * CONV_THREADS;
+            if (q < nchunks) {
+              const int row = q >> 3, oc = q & 7, sw = row & 7;
+              const uint32_t rb = raw + (oc >> 2) * a_plane + row * 128;
+              const int c0 = (oc & 3) * 2;
+              x0[u] = lds128f(rb + ((c0 ^ sw) << 4));
+              x1[u] = lds128f(rb + (((c0 + 1) ^ sw) << 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int q = q0 + u * CONV_THREADS;
+            if (q < nchunks) {
+              const int row = q >> 3, oc = q & 7, sw = row & 7;
+              float x[8] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w, x1[u].x, x1[u].y, x1[u].z, x1[u].w};
+              if (pro) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = prelu(x[i], alpha_in);
+              }
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              const uint32_t off = row * 128 + ((oc ^ sw) << 4);
+              sts128(dst + off, hi);
+              sts128(dst + a_plane + off, lo);
+            }
+          }
         }
       }
       fence_proxy_async();  // make the generic-proxy writes visible to the tensor core (async proxy)
       mbar_arrive(full + s);
-      if (tg == 0 && kb < 16) TR(40 + kb);   // stage published
+      mbar_arrive(raw_empty + r);
+      if (t == 0 && kb < 16) TR(40 + kb);
     }
 
     // ---- epilogue: TMEM -> registers -> global; lane = output channel, column = frame ----
@@ -501,8 +551,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     };
     // software pipeline: the TMEM loads of the next 8 columns are in flight while this chunk is processed
     if (jb < je) issue(rawA, jb);
+    if (t == 0) TR(6);
     for (int j = jb; j < je; j += 16) {
       tmem_ld_wait();
+      if (t == 0 && j == jb) TR(7);
       if (j + 8 < je) issue(rawB, j + 8);
       process(rawA, j);
       if (j + 8 < je) {
@@ -794,13 +846,26 @@ static int make_plane_map(CUtensorMap* map, const void* plane, int rows, int col
   return 0;
 }
 
+static size_t tc_gemm_tail_bytes() { return (2 * STAGES + 2 * RAW_STAGES + 1) * 8 + 8 + 256 * 4 * 3; }
+static int tc_gemm_raw_stages(int NF, bool tf32) {
+  const size_t stage = 2 * W_PLANE_BYTES + 2 * (size_t)NF * 128, raw = (size_t)NF * 128 * (tf32 ? 1 : 2);
+  const size_t budget = 227 * 1024 - tc_gemm_tail_bytes();
+  if (budget < STAGES * stage) return 0;
+  int rst = (int)((budget - STAGES * stage) / raw);
+  return rst > RAW_STAGES ? RAW_STAGES : rst;
+}
+static size_t tc_gemm_smem(int NF, bool tf32, int raw_stages) {
+  return (size_t)STAGES * (2 * W_PLANE_BYTES + 2 * NF * 128) + (size_t)raw_stages * NF * 128 * (tf32 ? 1 : 2) +
+         tc_gemm_tail_bytes();
+}
+
 static int pick_nf(int64_t F, int o_tiles, bool tf32) {
   // frames per tile (multiple of 16, <= 256) minimising (waves * tile time) on 148 SMs; the TF32 flavour needs room
   // for >= 2 main accumulators + 1 correction accumulator in the 512 TMEM columns
   int best = 128;
   double best_cost = 1e30;
-  (void)tf32;  // both flavours: NF <= 160 (TMEM room for the split accumulators; converter register budget)
-  for (int nf = 64; nf <= 160; nf += 16) {
+  for (int nf = 64; nf <= (tf32 ? 160 : 256); nf += 16) {
+    if (tc_gemm_raw_stages(nf, tf32) < 2) continue;  // operand stages + raw ring must fit in 227 KB
     const int64_t tiles = (F + nf - 1) / nf * o_tiles;
     const int64_t waves = (tiles + 147) / 148;
     const double cost = (double)waves * (nf + 40);  // + fixed per-tile overhead (prologue/epilogue)
@@ -812,14 +877,19 @@ static int pick_nf(int64_t F, int o_tiles, bool tf32) {
   return best;
 }
 
-static int tc_gemm_stages(int NF) {
-  const size_t stage = 2 * W_PLANE_BYTES + 2 * (size_t)NF * 128;
-  const size_t budget = 227 * 1024 - ((2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3);
-  int st = (int)(budget / stage);
-  return st > STAGES ? STAGES : st;
-}
-static size_t tc_gemm_smem(int NF, int stages) {
-  return (size_t)stages * (2 * W_PLANE_BYTES + 2 * NF * 128) + (2 * STAGES + 1) * 8 + 8 + 256 * 4 * 3;
+// fp32 activation matrix [F, Kd] row-major -> tensor map with a [NF rows x 32 floats] box, 128-byte swizzle, zero fill
+static int make_act_map(CUtensorMap* map, const float* A, int64_t F, int Kd, int NF) {
+  EncodeTiledFn enc = get_encode();
+  CTN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)Kd, (cuuint64_t)F};
+  const cuuint64_t strides[1] = {(cuuint64_t)Kd * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)NF};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CTN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (activations) failed with code %d", (int)r);
+  return 0;
 }
 
 }  // namespace
@@ -842,9 +912,12 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (a.groups > 4) a.groups = 4;
   a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
   a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
-  a.stages = tc_gemm_stages(a.NF);
-  const size_t smem = tc_gemm_smem(a.NF, a.stages);
-  CTN_REQUIRE(a.stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
+  a.stages = STAGES;
+  a.raw_stages = tc_gemm_raw_stages(a.NF, tf32);
+  const size_t smem = tc_gemm_smem(a.NF, tf32, a.raw_stages);
+  CUtensorMap ma;
+  CTN_TRY(make_act_map(&ma, g.A, g.F, g.Kd, a.NF));
+  CTN_REQUIRE(a.raw_stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
   dim3 grid(cdiv(g.F, a.NF), g.O / BM);
   const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
 #define CTN_TC_LAUNCH(TF, FO, RE, ST)                                                                            \
@@ -855,7 +928,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
                                     227 * 1024));                                                                \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    tc_gemm_kernel<TF, FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, a);                                    \
+    tc_gemm_kernel<TF, FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, ma, a);                                    \
   } while (0)
   if (tf32) {  // forward 1x1 convs
     if (!fold && !res && !stats) CTN_TC_LAUNCH(true, false, false, false);

@@ -22,6 +22,7 @@ print(' prologue done      ', np.median(col(1)))
 for kb in range(8): print(f' kb{kb}: loads issued {np.median(col(24+kb)):8.0f}  published {np.median(col(40+kb)):8.0f}  mma sees full {np.median(col(8+kb)):8.0f}')
 print(' mma all issued     ', np.median(col(2)))
 print(' tmem_full seen     ', np.median(col(3)))
+print(' epi first issue    ', np.median(col(6)), ' first wait done', np.median(col(7)))
 print(' epilogue done      ', np.median(col(4)))
 print(' exit               ', np.median(col(5)))
 print(' first-wave vs second-wave entry spread (cycles):', np.percentile(t[:,0]-t[:,0].min(), [0, 50, 56, 100]))
