@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run only warm-up + K device-resident steps (for ncu)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
+                    "one captured CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -234,14 +236,32 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / 1e3
 
+    # ---- one training step captured as a CUDA graph (conv_tasnet_b200.graph.GraphedTrainStep: the launch sequence is
+    # static — no host sync, no allocation in the C ABI, device-side step counter) and replayed per step ------------
+    from conv_tasnet_b200.graph import GraphedInference, GraphedTrainStep
+    use_graph = not args.no_graph and not args.profile_only
+    gstep = GraphedTrainStep(dp, opt) if use_graph else None
+    launches_per_step = 0
+    if gstep is not None:
+        n_before = L.ctn_launch_count()
+        gstep(mix_d, src_d, len_d)  # warm-up + capture
+        launches_per_step = (L.ctn_launch_count() - n_before) // (gstep.warmup + 1)
+        if not gstep.captured:
+            gstep = None
+
+    def run_step():
+        if gstep is not None:
+            return gstep(mix_d, src_d, len_d)
+        return step(mix_d, src_d, len_d)
+
     # ---- device-resident throughput -------------------------------------------------------------------
     for _ in range(args.warmup):
-        step(mix_d, src_d, len_d)
+        run_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     n0 = L.ctn_launch_count()
-    secs = timed(lambda: step(mix_d, src_d, len_d), args.steps)
-    launches = L.ctn_launch_count() - n0
+    secs = timed(run_step, args.steps)
+    launches = (launches_per_step * args.steps) if gstep is not None else (L.ctn_launch_count() - n0)
     audio = world * M * T / SR * args.steps
     value = audio / secs
     if args.profile_only:
@@ -254,6 +274,9 @@ def main():
     losses = []
 
     def e2e_step():
+        if gstep is not None:  # H2D from pinned memory into the graph's static inputs, replay, D2H of the loss
+            losses.append(gstep(mix_h, src_h, len_h).item())
+            return
         mix = mix_h.to(dev, non_blocking=True)
         src = src_h.to(dev, non_blocking=True)
         lens = len_h.to(dev, non_blocking=True)
@@ -268,9 +291,10 @@ def main():
     # ---- forward-only throughput (the metric's other half) --------------------------------------------
     model.eval()
     with torch.no_grad():
+        infer = GraphedInference(dp) if use_graph else dp
         for _ in range(3):
-            dp(mix_d)
-        secs_fwd = timed(lambda: dp(mix_d), args.steps)
+            infer(mix_d)
+        secs_fwd = timed(lambda: infer(mix_d), args.steps)
     model.train()
 
     # ---- roofline of the dominant kernel: the 1x1-conv GEMM at its most frequent shape (B->H, F frames) --
@@ -323,7 +347,7 @@ def main():
             "e2e": {"value": audio / secs_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": secs_e2e / args.steps * 1e3, "last_loss": losses[-1]},
             "fwd": {"value": audio / secs_fwd, "unit": "audio-s/s", "ms_per_step": secs_fwd / args.steps * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "cuda_graph": gstep is not None, "clocks": clocks, "roofline": roofline,
             "step_algorithmic": {"tflops": step_flops / t_step / 1e12, "gbs": step_bytes / t_step / 1e9,
                                  "hbm_bound_ms": step_bytes / world / (pk["hbm_gbs"] * 1e9) * 1e3,
                                  "frac_of_hbm_bound": (step_bytes / world / (pk["hbm_gbs"] * 1e9)) / t_step}}

@@ -1,0 +1,97 @@
+"""CUDA-graph capture of the hot loop body (src/solver.py:188-196) and of inference.
+
+The C ABI launches a static sequence of kernels (no host sync, no allocation, device-side Adam step counter), so one
+training step — forward, PIT loss, backward, gradient all-reduce, clip, Adam — is captured once per input shape and
+replayed with a single graph launch; inputs are copied into the graph's static buffers (that copy is the H2D transfer
+when the caller hands over pinned host tensors)."""
+import torch
+
+from .pit_criterion import cal_loss
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(model_or_dp, optimizer); loss = step(mixture, source, lengths)
+
+    `optimizer` must be capturable (conv_tasnet_b200.optim.FusedAdam is).  Falls back to eager launches if capture is
+    refused (e.g. a collective backend that cannot be captured)."""
+
+    def __init__(self, model, optimizer, warmup=3):
+        self.model, self.optimizer, self.warmup = model, optimizer, warmup
+        self._shape, self._graph, self._static, self._loss = None, None, None, None
+        self.captured = False
+
+    def _eager(self, mix, src, lens):
+        est = self.model(mix)
+        loss, _, _, _ = cal_loss(src, est, lens)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _capture(self, mix, src, lens):
+        dev = mix.device
+        self._static = (torch.empty_like(mix, device=dev), torch.empty_like(src, device=dev),
+                        torch.empty_like(lens, device=dev))
+        for d, s in zip(self._static, (mix, src, lens)):
+            d.copy_(s)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._eager(*self._static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loss = self._eager(*self._static)
+            self._graph, self.captured = g, True
+        except Exception:  # capture refused: keep working, eagerly
+            torch.cuda.synchronize(dev)
+            self._graph, self.captured = None, False
+        self._shape = (tuple(mix.shape), tuple(src.shape))
+
+    def __call__(self, mixture, source, lengths):
+        if self._shape != (tuple(mixture.shape), tuple(source.shape)):
+            self._capture(mixture.to(self._device_of(), non_blocking=True), source.to(self._device_of(), non_blocking=True),
+                          torch.as_tensor(lengths).to(self._device_of(), non_blocking=True))
+        if self._graph is None:
+            dev = self._device_of()
+            return self._eager(mixture.to(dev, non_blocking=True), source.to(dev, non_blocking=True),
+                               torch.as_tensor(lengths).to(dev, non_blocking=True))
+        for d, s in zip(self._static, (mixture, source, lengths)):
+            if d.data_ptr() != (s.data_ptr() if isinstance(s, torch.Tensor) and s.is_cuda else -1):
+                d.copy_(torch.as_tensor(s), non_blocking=True)
+        self._graph.replay()
+        return self._loss
+
+    def _device_of(self):
+        m = getattr(self.model, "module", self.model)
+        return m.flat_params.device
+
+
+class GraphedInference:
+    """infer = GraphedInference(model); est = infer(mixture)   (est is a static buffer, overwritten by the next call)"""
+
+    def __init__(self, model):
+        self.model = model
+        self._shape, self._graph, self._in, self._out = None, None, None, None
+
+    def __call__(self, mixture):
+        if self._shape != tuple(mixture.shape):
+            m = getattr(self.model, "module", self.model)
+            dev = m.flat_params.device
+            self._in = torch.empty(mixture.shape, dtype=torch.float32, device=dev)
+            self._in.copy_(mixture)
+            with torch.no_grad():
+                for _ in range(2):
+                    self.model(self._in)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._out = self.model(self._in)
+            self._graph, self._shape = g, tuple(mixture.shape)
+        if self._in.data_ptr() != (mixture.data_ptr() if mixture.is_cuda else -1):
+            self._in.copy_(mixture, non_blocking=True)
+        self._graph.replay()
+        return self._out
