@@ -12,21 +12,30 @@ from .pit_criterion import cal_loss
 class GraphedTrainStep:
     """step = GraphedTrainStep(model_or_dp, optimizer); loss = step(mixture, source, lengths)
 
-    `optimizer` must be capturable (conv_tasnet_b200.optim.FusedAdam is).  Falls back to eager launches if capture is
-    refused (e.g. a collective backend that cannot be captured)."""
+    `optimizer` must be capturable (conv_tasnet_b200.optim.FusedAdam is).  Under data parallelism
+    (ShardedDataParallel) the collectives stay outside the graphs: graph 1 = forward + loss + backward, then the
+    bucketed NCCL all-reduce of the flat gradient buffer is launched eagerly, then graph 2 = clip + Adam.
+    Falls back to eager launches if capture is refused."""
 
     def __init__(self, model, optimizer, warmup=3):
         self.model, self.optimizer, self.warmup = model, optimizer, warmup
-        self._shape, self._graph, self._static, self._loss = None, None, None, None
+        self._shape, self._graph, self._graph2, self._static, self._loss = None, None, None, None, None
         self.captured = False
 
-    def _eager(self, mix, src, lens):
+    def _fwd_bwd(self, mix, src, lens):
         est = self.model(mix)
         loss, _, _, _ = cal_loss(src, est, lens)
         self.optimizer.zero_grad()
         loss.backward()
+        return loss
+
+    def _eager(self, mix, src, lens):
+        loss = self._fwd_bwd(mix, src, lens)
         self.optimizer.step()
         return loss
+
+    def _dp(self):
+        return self.model if getattr(self.model, "_enabled", False) and hasattr(self.model, "all_reduce_flat") else None
 
     def _capture(self, mix, src, lens):
         dev = mix.device
@@ -41,14 +50,29 @@ class GraphedTrainStep:
                 self._eager(*self._static)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        dp = self._dp()
         try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._loss = self._eager(*self._static)
-            self._graph, self.captured = g, True
+            if dp is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._loss = self._eager(*self._static)
+                self._graph, self._graph2 = g, None
+            else:  # collectives stay eager, between two graphs
+                hook, dp.module._grad_sync = dp.module._grad_sync, None
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._loss = self._fwd_bwd(*self._static)
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        self.optimizer.step()
+                finally:
+                    dp.module._grad_sync = hook
+                self._graph, self._graph2 = g, g2
+            self.captured = True
         except Exception:  # capture refused: keep working, eagerly
             torch.cuda.synchronize(dev)
-            self._graph, self.captured = None, False
+            self._graph, self._graph2, self.captured = None, None, False
         self._shape = (tuple(mix.shape), tuple(src.shape))
 
     def __call__(self, mixture, source, lengths):
@@ -63,6 +87,9 @@ class GraphedTrainStep:
             if d.data_ptr() != (s.data_ptr() if isinstance(s, torch.Tensor) and s.is_cuda else -1):
                 d.copy_(torch.as_tensor(s), non_blocking=True)
         self._graph.replay()
+        if self._graph2 is not None:
+            self._dp().all_reduce_flat()
+            self._graph2.replay()
         return self._loss
 
     def _device_of(self):
