@@ -196,6 +196,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT at VERSION/INFO level; stdout carries exactly one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("CTN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
