@@ -120,6 +120,16 @@ struct GemmArgs {
   const void* W_hi;
   const void* W_lo;
   int tf32;  // 1: planes are fp32 (tf32 hi + exact remainder), forward precision; 0: bf16 hi/lo planes
+  // optional fused norm-backward reduction on the OUTPUT (D = dn, the gradient w.r.t. a normalised activation):
+  // with yhat = (prelu(nred_z, nred_alpha) - mu) * r (stats in `st`):  dgamma[o] += sum_f D*yhat, dbeta[o] += sum_f D,
+  // red[m] += (sum D*gamma, sum D*gamma*yhat).  nred_part: scratch for the un-fused fallback.
+  const float* nred_z;
+  const float* nred_alpha;
+  const float* nred_gamma;
+  float* nred_dgamma;
+  float* nred_dbeta;
+  double* nred_red;
+  float* nred_part;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t s);
 

@@ -251,6 +251,12 @@ struct TcGemmArgs {
   const float* res;
   double* stat_out;
   const float* alpha_out;
+  const float* nred_z;
+  const float* nred_alpha;
+  const float* nred_gamma;
+  float* nred_dgamma;
+  float* nred_dbeta;
+  double* nred_red;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -262,7 +268,7 @@ struct TcGemmArgs {
 // Warp roles: 0 = TMA producer of the weight planes, 3 = TMA producer of the raw activation tiles, 1 = MMA issuer,
 // 2 = TMEM allocator, 4..11 = converters (smem raw fp32 -> prologue -> hi/lo split -> swizzled operand planes; no global
 // loads, so nothing is in flight when they fence) and afterwards the epilogue.
-template <bool TF32, bool FOLD, bool RES, bool STATS>
+template <bool TF32, bool FOLD, bool RES, bool STATS, bool NRED = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_a, TcGemmArgs a) {
@@ -460,7 +466,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       float mu = 0.f, r = 1.f;
       if (t < nvalid) {
         m = (int)((uint32_t)(f0 + t) / (uint32_t)a.K);
-        if (FOLD) load_stats(a.st, m, f0 + t, mu, r);
+        if (FOLD || NRED) load_stats(a.st, m, f0 + t, mu, r);
       }
       s_m[t] = m;
       s_col[t] = make_float2(r, mu * r);
@@ -481,7 +487,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const uint32_t col_s = smem_u32(s_col);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float s1 = 0.f, s2 = 0.f;
-    int cur_m = STATS && jb < je ? s_m[jb] : -1;
+    int cur_m = (STATS || NRED) && jb < je ? s_m[jb] : -1;
+    const float* zptr = NRED ? a.nred_z + f0 * O + o : nullptr;
+    const float nr_alpha = (NRED && a.nred_alpha) ? __ldg(a.nred_alpha) : 1.f;
+    const bool nr_prelu = NRED && a.nred_alpha != nullptr;
+    const float nr_gamma = NRED ? __ldg(a.nred_gamma + o) : 0.f;
+    float nr_dg = 0.f, nr_db = 0.f;
     constexpr int NACC = TF32 ? 5 : 1;  // TMEM tiles summed per output (NG main + 1 correction, NG <= 4)
     uint32_t rawA[NACC][8], rawB[NACC][8];
     auto issue = [&](uint32_t (&dst)[NACC][8], int j) {
@@ -500,12 +511,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(cur[gidx][i]);
         }
       const int nj = min(8, je - j);
-      const bool uniform = !STATS || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
+      const bool uniform = !(STATS || NRED) || (s_m[j] == cur_m && s_m[j + nj - 1] == cur_m);
       if (nj == 8 && uniform) {  // fast path: whole chunk valid, one sample
         float resv[8];
         if (RES) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) resv[i] = __ldg(rptr + (j + i) * O);
+        }
+        if (NRED) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) resv[i] = __ldg(zptr + (j + i) * O);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -521,6 +536,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             s1 += p;
             s2 = fmaf(p, p, s2);
           }
+          if (NRED) {
+            const float2 cm = lds64(col_s + (j + i) * 8);
+            const float av = nr_prelu ? prelu(resv[i], nr_alpha) : resv[i];
+            const float yh = fmaf(av, cm.x, -cm.y);
+            nr_dg = fmaf(val, yh, nr_dg);
+            nr_db += val;
+            const float gh = val * nr_gamma;
+            s1 += gh;
+            s2 = fmaf(gh, yh, s2);
+          }
         }
       } else {  // chunk crosses the end of the tile or a sample boundary (at most a couple per tile)
         for (int i = 0; i < nj; ++i) {
@@ -531,20 +556,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           }
           if (RES) val += __ldg(rptr + (j + i) * O);
           dptr[(j + i) * O] = val;
-          if (STATS) {
+          if (STATS || NRED) {
             const int m = s_m[j + i];
             if (m != cur_m) {  // warp-uniform
               const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
-              if (lane == 0) {
-                atomicAdd(a.stat_out + 2 * cur_m, d1);
-                atomicAdd(a.stat_out + 2 * cur_m + 1, d2);
+              double* sacc = NRED ? a.nred_red : a.stat_out;
+              if (lane == 0 && sacc != nullptr) {
+                atomicAdd(sacc + 2 * cur_m, d1);
+                atomicAdd(sacc + 2 * cur_m + 1, d2);
               }
               cur_m = m;
               s1 = s2 = 0.f;
             }
+          }
+          if (STATS) {
             const float p = prelu(val, alpha_out);
             s1 += p;
             s2 = fmaf(p, p, s2);
+          }
+          if (NRED) {
+            const float2 cm = lds64(col_s + (j + i) * 8);
+            const float zv = __ldg(zptr + (j + i) * O);
+            const float av = nr_prelu ? prelu(zv, nr_alpha) : zv;
+            const float yh = fmaf(av, cm.x, -cm.y);
+            nr_dg = fmaf(val, yh, nr_dg);
+            nr_db += val;
+            const float gh = val * nr_gamma;
+            s1 += gh;
+            s2 = fmaf(gh, yh, s2);
           }
         }
       }
@@ -563,12 +602,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         process(rawB, j + 8);
       }
     }
-    if (STATS && cur_m >= 0) {
+    if ((STATS || NRED) && cur_m >= 0) {
       const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
-      if (lane == 0) {
-        atomicAdd(a.stat_out + 2 * cur_m, d1);
-        atomicAdd(a.stat_out + 2 * cur_m + 1, d2);
+      double* sacc = NRED ? a.nred_red : a.stat_out;
+      if (lane == 0 && sacc != nullptr) {
+        atomicAdd(sacc + 2 * cur_m, d1);
+        atomicAdd(sacc + 2 * cur_m + 1, d2);
       }
+    }
+    if (NRED) {  // per-channel partial sums of this tile's frames
+      atomicAdd(a.nred_dgamma + o, nr_dg);
+      atomicAdd(a.nred_dbeta + o, nr_db);
     }
   }
   if (threadIdx.x == 128) TR(4);
@@ -912,6 +956,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   if (a.groups > 4) a.groups = 4;
   a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
   a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
+  a.nred_z = g.nred_z; a.nred_alpha = g.nred_alpha; a.nred_gamma = g.nred_gamma;
+  a.nred_dgamma = g.nred_dgamma; a.nred_dbeta = g.nred_dbeta; a.nred_red = g.nred_red;
   a.stages = STAGES;
   a.raw_stages = tc_gemm_raw_stages(a.NF, tf32);
   const size_t smem = tc_gemm_smem(a.NF, tf32, a.raw_stages);
@@ -920,15 +966,15 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   CTN_REQUIRE(a.raw_stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
   dim3 grid(cdiv(g.F, a.NF), g.O / BM);
   const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
-#define CTN_TC_LAUNCH(TF, FO, RE, ST)                                                                            \
+#define CTN_TC_LAUNCH(...)                                                                                       \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
     if (!attr_set) {                                                                                             \
-      CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TF, FO, RE, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                     227 * 1024));                                                                \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    tc_gemm_kernel<TF, FO, RE, ST><<<grid, TC_THREADS, smem, s>>>(mh, ml, ma, a);                                    \
+    tc_gemm_kernel<__VA_ARGS__><<<grid, TC_THREADS, smem, s>>>(mh, ml, ma, a);                                   \
   } while (0)
   if (tf32) {  // forward 1x1 convs
     if (!fold && !res && !stats) CTN_TC_LAUNCH(true, false, false, false);
@@ -937,7 +983,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
     else if (fold && res && !stats) CTN_TC_LAUNCH(true, true, true, false);
     else return launch_gemm_simt(g, s);  // combinations the model never issues
   } else {     // data gradients
-    if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false);
+    if (g.nred_z != nullptr && !fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false, true);
+    else if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false);
     else if (!fold && res && !stats) CTN_TC_LAUNCH(false, false, true, false);
     else return launch_gemm_simt(g, s);
   }

@@ -109,6 +109,19 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
   if (!tc_gemm_eligible(a)) return launch_gemm_simt(a0, s);
   return launch_gemm_tc(a, s);
 }
+
+// GEMM whose output is the gradient w.r.t. a normalised activation, plus the norm-backward reduction over that output:
+// fused into the tcgen05 epilogue when the shape is on the MMA grid, otherwise GEMM followed by norm_bwd_reduce
+static int launch_gemm_nred(const GemmArgs& a, int M, cudaStream_t s) {
+  const bool fused = !force_simt() && !env_flag("CTN_SIMT_BWD") && !env_flag("CTN_NO_NRED_FUSION") && a.W_hi != nullptr &&
+                     a.Kd % 64 == 0 && a.O % 128 == 0 && a.F >= 16;
+  if (fused) return launch_gemm(a, s);
+  GemmArgs b = a;
+  b.nred_z = nullptr;
+  CTN_TRY(launch_gemm(b, s));
+  return run_norm_bwd_reduce(a.D, a.nred_z, a.nred_alpha, a.st, a.nred_gamma, M, a.K, a.O, a.nred_dgamma, a.nred_dbeta,
+                             a.nred_red, a.nred_part, s);
+}
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   static const bool simt_bwd = env_flag("CTN_SIMT_BWD") || env_flag("CTN_SIMT_WGRAD");
   if (force_simt() || simt_bwd || !tc_wgrad_eligible(a)) return launch_wgrad_simt(a, s);
@@ -424,7 +437,11 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       a.A = g_cur; a.W = X.blk(b, L.W2); a.w_is_kn = 1; a.D = dn2; a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
       a.W_hi = X.at<char>(p.pl_W2T) + (int64_t)b * c.B * c.H * 2;
       a.W_lo = X.at<char>(p.pl_W2T + p.pl_lo) + (int64_t)b * c.B * c.H * 2;
-      CTN_TRY(launch_gemm(a, s));
+      // + norm2 backward reduction over dn2 (dgamma2, dbeta2, per-sample sums) in the same kernel
+      a.st = st2; a.nred_z = X.z2(b); a.nred_alpha = X.blk(b, L.a2); a.nred_gamma = X.blk(b, L.g2);
+      a.nred_dgamma = gblk(b, L.g2); a.nred_dbeta = gblk(b, L.b2); a.nred_red = gln ? X.red(b, 1) : nullptr;
+      a.nred_part = X.at<float>(p.part);
+      CTN_TRY(launch_gemm_nred(a, M, s));
     }
     {  // dW2 = g^T norm2(prelu(z2))
       WgradArgs wa = {};
@@ -432,8 +449,6 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       wa.alpha = X.blk(b, L.a2); wa.gamma = X.blk(b, L.g2); wa.beta = X.blk(b, L.b2); wa.st = st2;
       CTN_TRY(launch_wgrad(wa, s));
     }
-    CTN_TRY(run_norm_bwd_reduce(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), M, K, c.H, gblk(b, L.g2),
-                                gblk(b, L.b2), gln ? X.red(b, 1) : nullptr, X.at<float>(p.part), s));
     CTN_TRY(run_norm_bwd_apply(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), M, K, c.H,
                                gblk(b, L.a2), s));
     CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K, c.H,
