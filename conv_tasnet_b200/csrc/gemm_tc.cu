@@ -985,6 +985,9 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   } else {     // data gradients
     if (g.nred_z != nullptr && !fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false, true);
     else if (!fold && !res && !stats) CTN_TC_LAUNCH(false, false, false, false);
+    else if (!fold && !res && stats) CTN_TC_LAUNCH(false, false, false, true);   // inference-precision forward convs
+    else if (fold && !res && !stats) CTN_TC_LAUNCH(false, true, false, false);
+    else if (fold && res && !stats) CTN_TC_LAUNCH(false, true, true, false);
     else if (!fold && res && !stats) CTN_TC_LAUNCH(false, false, true, false);
     else return launch_gemm_simt(g, s);
   }

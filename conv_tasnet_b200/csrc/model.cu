@@ -320,15 +320,30 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
                             X.at<float>(p.c1b), X.at<float>(p.c2b), 0, 0, s));
   CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
                             X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
-  // tf32 hi / exact-remainder planes of every forward GEMM weight (batched over the blocks)
-  CTN_TRY(run_split_planes_tf32(X.blk(0, L.W1), (int64_t)c.H * c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
-                                X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, s));
-  CTN_TRY(run_split_planes_tf32(X.at<float>(p.W2g), (int64_t)c.B * c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
-                                X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, s));
-  CTN_TRY(run_split_planes_tf32(X.at<float>(p.Wbg), (int64_t)c.B * c.N, 1, 0, X.at<char>(p.pl_Wbg),
-                                X.at<char>(p.pl_Wbg + p.pl_lo), 0, s));
-  CTN_TRY(run_split_planes_tf32(X.params + L.Wm, (int64_t)c.C * c.N * c.B, 1, 0, X.at<char>(p.pl_Wm),
-                                X.at<char>(p.pl_Wm + p.pl_lo), 0, s));
+  // split planes of every forward GEMM weight (batched over the blocks).  Training: TF32 split (fp32-class forward,
+  // needed for gradient parity).  Inference: bf16 split — 1e-5-class outputs (budget 1e-4), half the
+  // tensor-core and shared-memory cost.
+  const int fwd_tf32 = p.training ? 1 : 0;
+  const int64_t esz = fwd_tf32 ? 4 : 2;
+  if (fwd_tf32) {
+    CTN_TRY(run_split_planes_tf32(X.blk(0, L.W1), (int64_t)c.H * c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
+                                  X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, s));
+    CTN_TRY(run_split_planes_tf32(X.at<float>(p.W2g), (int64_t)c.B * c.H, nblk, (int64_t)c.B * c.H,
+                                  X.at<char>(p.pl_W2g), X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, s));
+    CTN_TRY(run_split_planes_tf32(X.at<float>(p.Wbg), (int64_t)c.B * c.N, 1, 0, X.at<char>(p.pl_Wbg),
+                                  X.at<char>(p.pl_Wbg + p.pl_lo), 0, s));
+    CTN_TRY(run_split_planes_tf32(X.params + L.Wm, (int64_t)c.C * c.N * c.B, 1, 0, X.at<char>(p.pl_Wm),
+                                  X.at<char>(p.pl_Wm + p.pl_lo), 0, s));
+  } else {
+    CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
+                             X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, 0, s));
+    CTN_TRY(run_split_planes(X.at<float>(p.W2g), c.B, c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
+                             X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, 0, s));
+    CTN_TRY(run_split_planes(X.at<float>(p.Wbg), c.B, c.N, 1, 0, X.at<char>(p.pl_Wbg), X.at<char>(p.pl_Wbg + p.pl_lo),
+                             0, 0, s));
+    CTN_TRY(run_split_planes(X.params + L.Wm, c.C * c.N, c.B, 1, 0, X.at<char>(p.pl_Wm), X.at<char>(p.pl_Wm + p.pl_lo),
+                             0, 0, s));
+  }
   // encoder + first cLN statistics + bottleneck (cLN folded into the GEMM epilogue)
   float* w = X.at<float>(p.w);
   CTN_TRY(run_encoder_fwd(mixture, X.params + L.U, M, p.T, c.N, c.L, w, s));
@@ -338,7 +353,7 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
     a.A = w; a.W = X.at<float>(p.Wbg); a.D = X.x(0); a.F = F; a.O = c.B; a.Kd = c.N; a.K = K;
     a.c1 = X.at<float>(p.c1b); a.c2 = X.at<float>(p.c2b);
     a.st.row = X.at<float>(p.rowstat0);
-    a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo); a.tf32 = 1;
+    a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo); a.tf32 = fwd_tf32;
     CTN_TRY(launch_gemm(a, s));
   }
   for (int b = 0; b < nblk; ++b) {
@@ -347,9 +362,9 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       GemmArgs a = {};
       a.A = X.x(b); a.W = X.blk(b, L.W1); a.D = X.z1(b); a.F = F; a.O = c.H; a.Kd = c.B; a.K = K;
       a.stat_out = X.stat_out(b, 0); a.alpha_out = X.blk(b, L.a1);
-      a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * 4;
-      a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * 4;
-      a.tf32 = 1;
+      a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * esz;
+      a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * esz;
+      a.tf32 = fwd_tf32;
       CTN_TRY(launch_gemm(a, s));
     }
     if (!gln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
@@ -364,16 +379,16 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.c1 = X.at<float>(p.c1) + (int64_t)b * c.B; a.c2 = X.at<float>(p.c2) + (int64_t)b * c.B;
       a.st = X.stats(b, 1);
       a.res = X.x(b);
-      a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * 4;
-      a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * 4;
-      a.tf32 = 1;
+      a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * esz;
+      a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * esz;
+      a.tf32 = fwd_tf32;
       CTN_TRY(launch_gemm(a, s));
     }
   }
   {  // mask conv
     GemmArgs a = {};
     a.A = X.x(nblk); a.W = X.params + L.Wm; a.D = X.at<float>(p.score); a.F = F; a.O = c.C * c.N; a.Kd = c.B; a.K = K;
-    a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo); a.tf32 = 1;
+    a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo); a.tf32 = fwd_tf32;
     CTN_TRY(launch_gemm(a, s));
   }
   return run_decoder_fwd(X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,

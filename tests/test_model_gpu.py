@@ -34,8 +34,8 @@ def test_small_models_match_reference_golden(name):
     assert est.shape == tuple(z["est_source"].shape)
     assert rel_err(est.detach().cpu(), z["est_source"]) < 1e-4
     with torch.no_grad():
-        est_inf = model(mix)  # inference path (ping-pong buffers) must equal the training path (stash)
-    assert torch.equal(est_inf, est.detach())
+        est_inf = model(mix)  # inference path (ping-pong buffers; on MMA-grid shapes also the bf16 operand split)
+    assert rel_err(est_inf.cpu(), est.detach().cpu()) < 2e-5
     loss, max_snr, est_masked, reord = cal_loss(src, est, lens.cuda())
     assert abs(loss.item() - float(z["loss"])) < 0.01
     assert rel_err(max_snr.cpu(), z["max_snr"]) < 1e-4
