@@ -134,10 +134,21 @@ __global__ void __launch_bounds__(256) prep_normfold_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------
 // norm1 apply + dilated depthwise conv (+Chomp1d) (+ gLN stats of prelu(z2))
-// grid (frame tiles, M), block = H/4 threads rounded up to a warp (<= 256, loops over channel groups)
+// A block walks the frames k_j = r + j*d of one residue class r (mod dilation d): the P taps of output j are the
+// window elements j + p - cshift of that sequence, so each input row is loaded and normalised ONCE and slides through
+// a P-deep register window (instead of being re-read from L2 once per tap).
+// grid (classes * segments, M), block = H/4 threads rounded up to a warp (<= 256, loops over channel groups)
 // ---------------------------------------------------------------------------------------
-constexpr int DW_TK = 8;
+constexpr int DW_TJ = 16;  // outputs per block (per channel group)
+constexpr int DW_U = 4;    // outputs per inner group: DW_U independent loads in flight
 constexpr int MAXP = 8;
+
+__host__ __device__ inline int dw_classes(int K, int dil) { return dil < K ? dil : K; }
+__host__ __device__ inline int dw_blocks(int K, int dil) {
+  const int ncls = dw_classes(K, dil);
+  const int per_class = (K + ncls - 1) / ncls;  // frames in the largest class
+  return ncls * ((per_class + DW_TJ - 1) / DW_TJ);
+}
 
 template <int PT>
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ alpha1,
@@ -148,13 +159,16 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ alpha2) {
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
-  const int m = blockIdx.y, k0 = blockIdx.x * DW_TK;
-  const int nk = min(DW_TK, K - k0);
+  const int m = blockIdx.y;
+  const int ncls = dw_classes(K, dil);
+  const int r = blockIdx.x % ncls, j0 = (blockIdx.x / ncls) * DW_TJ;
+  const int nclass = (K - r + dil - 1) / dil;            // frames of this residue class
+  const int nj = max(0, min(DW_TJ, nclass - j0));        // outputs of this block
   if (st1.row == nullptr) {
     if (threadIdx.x == 0) {
-      float mu, r;
-      load_stats(st1, m, 0, mu, r);
-      s_st = make_float2(mu, r);
+      float mu, rr;
+      load_stats(st1, m, 0, mu, rr);
+      s_st = make_float2(mu, rr);
     }
     __syncthreads();
   }
@@ -162,52 +176,65 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
   const bool do_stats = stat_out != nullptr;
   const float a2 = do_stats ? __ldg(alpha2) : 1.f;
   const int64_t base = (int64_t)m * K;
+  constexpr int NP_ = PT ? PT : MAXP;
+  const int PP = PT ? PT : P;
   double acc[2] = {0.0, 0.0};
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
-    constexpr int NP_ = PT ? PT : MAXP;
-    const int PP = PT ? PT : P;
     float wd[4][NP_];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int p = 0; p < NP_; ++p) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
+    // normalised input of sequence index idx (zero outside [0, K): the padding is applied after the norm)
+    auto fetch = [&](int idx, float4& raw, float2& stv, bool& ok) {
+      const int k = r + idx * dil;
+      ok = idx >= 0 && k < K;
+      raw = ok ? ld4(z1 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      stv = (ok && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + k] : s_st;
+    };
+    auto normalise = [&](const float4& raw, const float2& stv, bool ok) {
+      if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = prelu4(raw, a1);
+      return make_float4(g.x * (v.x - stv.x) * stv.y + b.x, g.y * (v.y - stv.x) * stv.y + b.y,
+                         g.z * (v.z - stv.x) * stv.y + b.z, g.w * (v.w - stv.x) * stv.y + b.w);
+    };
+    float4 w[NP_];  // w[p] = normalised input at sequence index j + p - cshift for the current output j
+#pragma unroll
+    for (int p = 0; p < NP_; ++p) {
+      float4 raw; float2 stv; bool ok;
+      if (p < PP) { fetch(j0 + p - cshift, raw, stv, ok); w[p] = normalise(raw, stv, ok); }
+      else w[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; kk += 2) {
-      // all tap loads of two output frames first (ILP), then the math
-      float4 tv[2][NP_];
-      float2 stv[2][NP_];
-      bool ok[2][NP_];
+    for (int jj = 0; jj < nj; jj += DW_U) {
+      // the DW_U rows that enter the window after each of the next DW_U outputs: independent loads, issued together
+      float4 nraw[DW_U]; float2 nst[DW_U]; bool nok[DW_U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < DW_U; ++u) fetch(j0 + jj + u + PP - cshift, nraw[u], nst[u], nok[u]);
 #pragma unroll
-        for (int p = 0; p < NP_; ++p) {
-          const int ks = k0 + kk + u + (p - cshift) * dil;
-          ok[u][p] = p < PP && kk + u < nk && ks >= 0 && ks < K;  // zero padding is applied after the norm
-          tv[u][p] = ok[u][p] ? ld4(z1 + (base + ks) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          stv[u][p] = (ok[u][p] && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + ks] : s_st;
+      for (int u = 0; u < DW_U; ++u) {
+        if (jj + u < nj) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int p = 0; p < NP_; ++p) {
+            o.x = fmaf(wd[0][p], w[p].x, o.x); o.y = fmaf(wd[1][p], w[p].y, o.y);
+            o.z = fmaf(wd[2][p], w[p].z, o.z); o.w = fmaf(wd[3][p], w[p].w, o.w);
+          }
+          st4(z2 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c, o);
+          if (do_stats) {
+            const float4 q = prelu4(o, a2);
+            s += (q.x + q.y) + (q.z + q.w);
+            s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+          }
         }
-      }
+        // slide
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (kk + u >= nk) break;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p + 1 < NP_; ++p) w[p] = w[p + 1];
+        const float4 nv = normalise(nraw[u], nst[u], nok[u]);
 #pragma unroll
-        for (int p = 0; p < NP_; ++p) {
-          if (!ok[u][p]) continue;
-          const float mu = stv[u][p].x, r = stv[u][p].y;
-          const float4 v = prelu4(tv[u][p], a1);
-          o.x = fmaf(wd[0][p], g.x * (v.x - mu) * r + b.x, o.x);
-          o.y = fmaf(wd[1][p], g.y * (v.y - mu) * r + b.y, o.y);
-          o.z = fmaf(wd[2][p], g.z * (v.z - mu) * r + b.z, o.z);
-          o.w = fmaf(wd[3][p], g.w * (v.w - mu) * r + b.w, o.w);
-        }
-        st4(z2 + (base + k0 + kk + u) * H + c, o);
-        if (do_stats) {
-          const float4 q = prelu4(o, a2);
-          s += (q.x + q.y) + (q.z + q.w);
-          s2 += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
-        }
+        for (int p = 0; p < NP_; ++p)
+          if (p == PP - 1) w[p] = nv;
       }
     }
     acc[0] += (double)s;
@@ -224,9 +251,9 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
 
 // backward: dn1[k] = sum_p Wd[p] * dz2[k - off_p];  dWd[p] += dz2[k - off_p] * n1[k];
 // plus the per-channel / per-sample reductions the norm1 backward needs (dgamma1, dbeta1, red1).
-// Per-channel sums leave the block as one row of `part` ([P+2][H]: taps, dgamma, dbeta) — no atomics; a second
-// kernel (reduce_partials_kernel) folds the rows.
-constexpr int DWB_TK = 16;
+// Same stride-d walk as the forward: the taps of dz2 for input frame k_j are the sequence elements j + cshift - p, a
+// P-deep sliding register window; z1 is read once for the centre.  Per-channel sums leave the block as one row of
+// `part` ([P+2][H]: taps, dgamma, dbeta) — no atomics; reduce_partials_kernel folds the rows.
 template <int PT>
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict__ dz2, const float* __restrict__ z1,
                                                          const float* __restrict__ alpha1, NormStats st1,
@@ -236,13 +263,16 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
                                                          double* __restrict__ red1) {
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
-  const int m = blockIdx.y, k0 = blockIdx.x * DWB_TK;
-  const int nk = min(DWB_TK, K - k0);
+  const int m = blockIdx.y;
+  const int ncls = dw_classes(K, dil);
+  const int r = blockIdx.x % ncls, j0 = (blockIdx.x / ncls) * DW_TJ;
+  const int nclass = (K - r + dil - 1) / dil;
+  const int nj = max(0, min(DW_TJ, nclass - j0));
   if (st1.row == nullptr) {
     if (threadIdx.x == 0) {
-      float mu, r;
-      load_stats(st1, m, 0, mu, r);
-      s_st = make_float2(mu, r);
+      float mu, rr;
+      load_stats(st1, m, 0, mu, rr);
+      s_st = make_float2(mu, rr);
     }
     __syncthreads();
   }
@@ -262,48 +292,60 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
       for (int j = 0; j < 4; ++j) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
       dwd[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    auto fetch_dz = [&](int idx) {  // dz2 at sequence index idx, zero outside
+      const int k = r + idx * dil;
+      return (idx >= 0 && k < K) ? ld4(dz2 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // v[i] = dz2 at sequence index j + cshift - (PP-1) + i; tap p reads i = PP-1-p
+    float4 v[NP_];
+#pragma unroll
+    for (int i = 0; i < NP_; ++i) v[i] = i < PP ? fetch_dz(j0 + cshift - (PP - 1) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; kk += 2) {
-      // issue every load of two frames first (ILP), then compute
-      float4 zv[2], tv[2][NP_];
-      float2 stv[2];
+    for (int jj = 0; jj < nj; jj += DW_U) {
+      float4 nv[DW_U], zc[DW_U]; float2 stv[DW_U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k = k0 + kk + u;
-        const bool vk = kk + u < nk;
-        zv[u] = vk ? ld4(z1 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        stv[u] = (vk && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + k] : s_st;
-#pragma unroll
-        for (int p = 0; p < NP_; ++p) {
-          const int ko = k - (p - cshift) * dil;  // the output frame whose tap p read input frame k
-          tv[u][p] = (vk && p < PP && ko >= 0 && ko < K) ? ld4(dz2 + (base + ko) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int u = 0; u < DW_U; ++u) {
+        nv[u] = fetch_dz(j0 + jj + u + cshift + 1);  // enters the window after output jj+u
+        const int k = r + (j0 + jj + u) * dil;
+        const bool ok = jj + u < nj;
+        zc[u] = ok ? ld4(z1 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        stv[u] = (ok && st1.row != nullptr) ? reinterpret_cast<const float2*>(st1.row)[base + k] : s_st;
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (kk + u >= nk) break;
-        const int k = k0 + kk + u;
-        const float mu = stv[u].x, r = stv[u].y;
-        const float4 a = prelu4(zv[u], a1);
-        const float4 yh = make_float4((a.x - mu) * r, (a.y - mu) * r, (a.z - mu) * r, (a.w - mu) * r);
-        const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < DW_U; ++u) {
+        if (jj + u < nj) {
+          const float mu = stv[u].x, rr = stv[u].y;
+          const float4 a = prelu4(zc[u], a1);
+          const float4 yh = make_float4((a.x - mu) * rr, (a.y - mu) * rr, (a.z - mu) * rr, (a.w - mu) * rr);
+          const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int p = 0; p < NP_; ++p) {
-          const float4 v = tv[u][p];
-          d.x = fmaf(wd[0][p], v.x, d.x); d.y = fmaf(wd[1][p], v.y, d.y);
-          d.z = fmaf(wd[2][p], v.z, d.z); d.w = fmaf(wd[3][p], v.w, d.w);
-          dwd[p].x = fmaf(v.x, n1.x, dwd[p].x); dwd[p].y = fmaf(v.y, n1.y, dwd[p].y);
-          dwd[p].z = fmaf(v.z, n1.z, dwd[p].z); dwd[p].w = fmaf(v.w, n1.w, dwd[p].w);
+          for (int p = 0; p < NP_; ++p) {
+            if (p < PP) {
+              float4 t = v[0];
+#pragma unroll
+              for (int i = 1; i < NP_; ++i)
+                if (i == PP - 1 - p) t = v[i];
+              d.x = fmaf(wd[0][p], t.x, d.x); d.y = fmaf(wd[1][p], t.y, d.y);
+              d.z = fmaf(wd[2][p], t.z, d.z); d.w = fmaf(wd[3][p], t.w, d.w);
+              dwd[p].x = fmaf(t.x, n1.x, dwd[p].x); dwd[p].y = fmaf(t.y, n1.y, dwd[p].y);
+              dwd[p].z = fmaf(t.z, n1.z, dwd[p].z); dwd[p].w = fmaf(t.w, n1.w, dwd[p].w);
+            }
+          }
+          st4(dn1 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c, d);
+          dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+          dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+          db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+          const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+          s += (gh.x + gh.y) + (gh.z + gh.w);
+          s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
         }
-        st4(dn1 + (base + k) * H + c, d);
-        dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
-        dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
-        db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
-        const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        s += (gh.x + gh.y) + (gh.z + gh.w);
-        s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
+#pragma unroll
+        for (int i = 0; i + 1 < NP_; ++i) v[i] = v[i + 1];
+#pragma unroll
+        for (int i = 0; i < NP_; ++i)
+          if (i == PP - 1) v[i] = nv[u];
       }
     }
 #pragma unroll
@@ -735,7 +777,7 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
   CTN_REQUIRE(P >= 1 && P <= MAXP, "dwconv: kernel size P must be in [1,%d] (got %d)", MAXP, P);
   CTN_REQUIRE(causal || (P % 2 == 1), "dwconv: non-causal needs odd P (reference output length changes otherwise)");
   const int cshift = causal ? P - 1 : (P - 1) / 2;
-  const dim3 grid(cdiv(K, DW_TK), M);
+  const dim3 grid(dw_blocks(K, dil), M);
   if (P == 3)
     dwconv_fwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift,
                                                                z2, stat_out, alpha2);
@@ -753,7 +795,9 @@ static int fold_partials(const float* part, int nb, int H, int P, float* dW, flo
   return check_launch("reduce_partials_kernel");
 }
 
-int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P) { return (int64_t)cdiv(K, DWB_TK) * M * (P + 2) * H; }
+int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P, int dil) {
+  return (int64_t)dw_blocks(K, dil) * M * (P + 2) * H;
+}
 int64_t norm_bwd_partial_floats(int M, int K, int Ch) { return (int64_t)cdiv(K, NR_TK) * M * 2 * Ch; }
 
 int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormStats st1, const float* gamma1,
@@ -762,11 +806,11 @@ int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormS
   CTN_REQUIRE(H % 4 == 0 && P >= 1 && P <= MAXP, "dwconv_bwd: bad H/P (%d/%d)", H, P);
   if (part == nullptr) {  // standalone call: library-owned scratch
     void* scr = nullptr;
-    CTN_TRY(lib_scratch((size_t)dwconv_bwd_partial_floats(M, K, H, P) * 4, &scr, 1));
+    CTN_TRY(lib_scratch((size_t)dwconv_bwd_partial_floats(M, K, H, P, dil) * 4, &scr, 1));
     part = reinterpret_cast<float*>(scr);
   }
   const int cshift = causal ? P - 1 : (P - 1) / 2;
-  const dim3 grid(cdiv(K, DWB_TK), M);
+  const dim3 grid(dw_blocks(K, dil), M);
   if (P == 3)
     dwconv_bwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
                                                                cshift, dn1, part, red1);

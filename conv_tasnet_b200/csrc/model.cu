@@ -44,7 +44,7 @@ int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const fl
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
                         float*, double*, float*, cudaStream_t);
-int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P);
+int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P, int dil);
 int64_t norm_bwd_partial_floats(int M, int K, int Ch);
 int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
                        float*, cudaStream_t);
@@ -250,7 +250,11 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
     p.dn0 = take(F * c.N * 4);
     p.red = take((int64_t)(p.nblk * 2 + 1) * M * 2 * 8);
     {
-      int64_t pf = dwconv_bwd_partial_floats(M, p.K, c.H, c.P);
+      int64_t pf = 0;
+      for (int x = 0; x < c.X; ++x) {
+        const int64_t q = dwconv_bwd_partial_floats(M, p.K, c.H, c.P, 1 << x);
+        pf = pf > q ? pf : q;
+      }
       const int64_t a = norm_bwd_partial_floats(M, p.K, c.H), b = norm_bwd_partial_floats(M, p.K, c.N);
       pf = pf > a ? pf : a;
       pf = pf > b ? pf : b;
