@@ -42,29 +42,35 @@ __global__ void __launch_bounds__(256) encoder_fwd_kernel(const float* __restric
   }
 }
 
-// dU[n,l] += sum_{f in tile} (dwa+dwb)[f,n] * [w[f,n] > 0] * mix[m, k*S+l]
+// dU[n,l] += sum_{f in tile} (dwa+dwb)[f,n] * [w[f,n] > 0] * mix[m, k*S+l]   (thread per n, accumulators in registers)
 constexpr int ENCB_TK = 32;
+constexpr int ENC_MAXL = 32;
 __global__ void __launch_bounds__(256) encoder_bwd_kernel(const float* __restrict__ mix, const float* __restrict__ w,
                                                           const float* __restrict__ dwa, const float* __restrict__ dwb,
                                                           int T, int K, int N, int L, float* __restrict__ dU) {
   extern __shared__ float sm[];
-  float* acc = sm;          // [L][N]
-  float* xs = sm + L * N;   // [ENCB_TK*S + L]
+  float* xs = sm;  // [ENCB_TK*S + L]
   const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENCB_TK;
   const int nk = min(ENCB_TK, K - k0);
-  for (int i = threadIdx.x; i < N * L; i += blockDim.x) acc[i] = 0.f;
   const int nx = (nk - 1) * S + L;
   for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = mix[(int64_t)m * T + (int64_t)k0 * S + i];
   __syncthreads();
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc[ENC_MAXL];
+#pragma unroll
+    for (int l = 0; l < ENC_MAXL; ++l) acc[l] = 0.f;
     for (int k = 0; k < nk; ++k) {
       const int64_t idx = ((int64_t)m * K + k0 + k) * N + n;
       float g = dwa[idx];
       if (dwb != nullptr) g += dwb[idx];
       if (!(w[idx] > 0.f)) g = 0.f;
-      for (int l = 0; l < L; ++l) acc[l * N + n] = fmaf(g, xs[k * S + l], acc[l * N + n]);
+#pragma unroll
+      for (int l = 0; l < ENC_MAXL; ++l)
+        if (l < L) acc[l] = fmaf(g, xs[k * S + l], acc[l]);
     }
-    for (int l = 0; l < L; ++l) atomicAdd(dU + n * L + l, acc[l * N + n]);
+#pragma unroll
+    for (int l = 0; l < ENC_MAXL; ++l)
+      if (l < L) atomicAdd(dU + n * L + l, acc[l]);
   }
 }
 
@@ -574,59 +580,63 @@ __global__ void __launch_bounds__(256) cln_bwd_apply_kernel(float* __restrict__ 
 // grid (frame tiles, M); one warp per frame computes frames[k][c][l]; then the block writes its
 // span of output samples (each sample sums the <= ceil(L/S) frames that cover it, ascending k).
 // ---------------------------------------------------------------------------------------
-constexpr int DEC_TK = 32;
+constexpr int DEC_TK = 8;
 constexpr int MAXC = 4;
+constexpr int DEC_MAXN = 16;  // per-lane basis channels (N <= 512)
 __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ score, const float* __restrict__ w,
                                                           const float* __restrict__ V, int K, int C, int N, int L,
                                                           int T, int softmax, float* __restrict__ est) {
   extern __shared__ float sm[];
   const int S = L / 2;
   const int halo = (L - 1) / S;  // frames before the tile that still reach into it
-  const int NP = N + 1;          // padded row: lanes with different l hit different banks
-  float* Vs = sm;                               // [L][N+1]
-  float* fr = Vs + L * NP;                      // [(DEC_TK + halo)][C][L]
-  float* sws = fr + (DEC_TK + halo) * C * L;    // [warps][C][N]  masked mixture weights of the warp's frame
+  float* Vs = sm;                               // [L][N]
+  float* fr = Vs + L * N;                       // [(DEC_TK + halo)][C][L]
   const int m = blockIdx.y, k0 = blockIdx.x * DEC_TK;
   const int kb = max(0, k0 - halo), ke = min(K, k0 + DEC_TK);
-  for (int i = threadIdx.x; i < L * N; i += blockDim.x) Vs[(i / N) * NP + (i % N)] = V[i];
+  for (int i = threadIdx.x; i < L * N; i += blockDim.x) Vs[i] = V[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float* sw = sws + wid * C * N;
-  for (int k = kb + wid; k < ke; k += nw) {
+  for (int k = kb + wid; k < ke; k += nw) {  // one frame per warp: lanes own n = lane + 32 i
     const int64_t f = (int64_t)m * K + k;
-    for (int n = lane; n < N; n += 32) {
-      const float wv = w[f * N + n];
-      float sc[MAXC];
+    float sw[MAXC][DEC_MAXN];
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) sc[c] = c < C ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
+    for (int i = 0; i < DEC_MAXN; ++i) {
+      const int n = lane + 32 * i;
+      float sc[MAXC];
+      const float wv = n < N ? w[f * N + n] : 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) sc[c] = (c < C && n < N) ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
       if (softmax) {
         float mx = sc[0];
 #pragma unroll
         for (int c = 1; c < MAXC; ++c) mx = fmaxf(mx, sc[c]);
         float den = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) { sc[c] = c < C ? expf(sc[c] - mx) : 0.f; den += sc[c]; }
+        for (int c = 0; c < MAXC; ++c) { sc[c] = (c < C && n < N) ? expf(sc[c] - mx) : 0.f; den += sc[c]; }
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) sc[c] = sc[c] / den * wv;
+        for (int c = 0; c < MAXC; ++c) sw[c][i] = n < N ? sc[c] / den * wv : 0.f;
       } else {
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) sc[c] = fmaxf(sc[c], 0.f) * wv;
+        for (int c = 0; c < MAXC; ++c) sw[c][i] = fmaxf(sc[c], 0.f) * wv;
       }
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c)
-        if (c < C) sw[c * N + n] = sc[c];
     }
-    __syncwarp();
     float* out = fr + (k - kb) * C * L;
-    for (int i = lane; i < C * L; i += 32) {
-      const int c = i / L, l = i - c * L;
-      const float* swc = sw + c * N;
-      const float* vl = Vs + l * NP;
-      float acc = 0.f;
-      for (int n = 0; n < N; ++n) acc = fmaf(swc[n], vl[n], acc);
-      out[i] = acc;
+    for (int c = 0; c < C; ++c) {
+      for (int l = 0; l < L; ++l) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < DEC_MAXN; ++i) {
+          const int n = lane + 32 * i;
+          float swv = sw[0][i];
+#pragma unroll
+          for (int cc = 1; cc < MAXC; ++cc)
+            if (cc == c) swv = sw[cc][i];
+          if (n < N) acc = fmaf(swv, Vs[l * N + n], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[c * L + l] = acc;
+      }
     }
-    __syncwarp();
   }
   __syncthreads();
   // output span of this tile: [k0*S, (k0+DEC_TK)*S), the last tile runs to T (tail + zero pad)
@@ -647,8 +657,10 @@ __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restric
   }
 }
 
-// Decoder backward: thread per basis channel n, loop over the tile's frames.
+// Decoder backward: thread per basis channel n (its V column and dV accumulators live in registers), loop over the
+// tile's frames.
 constexpr int DECB_TK = 32;
+constexpr int DEC_MAXL = 32;
 __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restrict__ d_est, const float* __restrict__ score,
                                                           const float* __restrict__ w, const float* __restrict__ V, int K,
                                                           int C, int N, int L, int T, int softmax,
@@ -656,54 +668,77 @@ __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restric
                                                           float* __restrict__ dV) {
   extern __shared__ float sm[];
   const int S = L / 2;
-  float* Vs = sm;                 // [L][N]
-  float* dVs = sm + L * N;        // [L][N]
-  float* df = sm + 2 * L * N;     // [DECB_TK][C][L]
+  float* df = sm;  // [DECB_TK][C][L]
   const int m = blockIdx.y, k0 = blockIdx.x * DECB_TK;
   const int nk = min(DECB_TK, K - k0);
-  for (int i = threadIdx.x; i < L * N; i += blockDim.x) { Vs[i] = V[i]; dVs[i] = 0.f; }
   for (int i = threadIdx.x; i < nk * C * L; i += blockDim.x) {
     const int l = i % L, c = (i / L) % C, kk = i / (L * C);
     df[i] = d_est[((int64_t)m * C + c) * T + (int64_t)(k0 + kk) * S + l];
   }
   __syncthreads();
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float vcol[DEC_MAXL], dvacc[DEC_MAXL];
+#pragma unroll
+    for (int l = 0; l < DEC_MAXL; ++l) {
+      vcol[l] = l < L ? V[l * N + n] : 0.f;
+      dvacc[l] = 0.f;
+    }
     for (int kk = 0; kk < nk; ++kk) {
       const int64_t f = (int64_t)m * K + k0 + kk;
       const float wv = w[f * N + n];
       float sc[MAXC], mk[MAXC], dsw[MAXC];
-      for (int c = 0; c < C; ++c) sc[c] = score[f * (int64_t)(C * N) + c * N + n];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) sc[c] = c < C ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
       if (softmax) {
         float mx = sc[0];
-        for (int c = 1; c < C; ++c) mx = fmaxf(mx, sc[c]);
+#pragma unroll
+        for (int c = 1; c < MAXC; ++c) mx = fmaxf(mx, sc[c]);
         float den = 0.f;
-        for (int c = 0; c < C; ++c) { mk[c] = expf(sc[c] - mx); den += mk[c]; }
-        for (int c = 0; c < C; ++c) mk[c] /= den;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) { mk[c] = c < C ? expf(sc[c] - mx) : 0.f; den += mk[c]; }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) mk[c] /= den;
       } else {
-        for (int c = 0; c < C; ++c) mk[c] = fmaxf(sc[c], 0.f);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) mk[c] = fmaxf(sc[c], 0.f);
       }
       float dwv = 0.f;
-      for (int c = 0; c < C; ++c) {
-        const float* dfc = df + (kk * C + c) * L;
-        const float sw = mk[c] * wv;
-        float acc = 0.f;
-        for (int l = 0; l < L; ++l) {
-          acc = fmaf(dfc[l], Vs[l * N + n], acc);
-          dVs[l * N + n] = fmaf(dfc[l], sw, dVs[l * N + n]);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        dsw[c] = 0.f;
+        if (c < C) {
+          const float* dfc = df + (kk * C + c) * L;
+          const float sw = mk[c] * wv;
+          float acc = 0.f;
+#pragma unroll
+          for (int l = 0; l < DEC_MAXL; ++l) {
+            if (l < L) {
+              const float d = dfc[l];
+              acc = fmaf(d, vcol[l], acc);
+              dvacc[l] = fmaf(d, sw, dvacc[l]);
+            }
+          }
+          dsw[c] = acc;
+          dwv = fmaf(acc, mk[c], dwv);
         }
-        dsw[c] = acc;
-        dwv = fmaf(acc, mk[c], dwv);
       }
       d_w[f * N + n] = dwv;
       if (softmax) {
         float dot = 0.f;
-        for (int c = 0; c < C; ++c) dot = fmaf(dsw[c] * wv, mk[c], dot);
-        for (int c = 0; c < C; ++c) d_score[f * (int64_t)(C * N) + c * N + n] = mk[c] * (dsw[c] * wv - dot);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) dot = fmaf(dsw[c] * wv, mk[c], dot);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < C) d_score[f * (int64_t)(C * N) + c * N + n] = mk[c] * (dsw[c] * wv - dot);
       } else {
-        for (int c = 0; c < C; ++c) d_score[f * (int64_t)(C * N) + c * N + n] = sc[c] > 0.f ? dsw[c] * wv : 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < C) d_score[f * (int64_t)(C * N) + c * N + n] = sc[c] > 0.f ? dsw[c] * wv : 0.f;
       }
     }
-    for (int l = 0; l < L; ++l) atomicAdd(dV + l * N + n, dVs[l * N + n]);
+#pragma unroll
+    for (int l = 0; l < DEC_MAXL; ++l)
+      if (l < L) atomicAdd(dV + l * N + n, dvacc[l]);
   }
 }
 
@@ -751,7 +786,8 @@ int run_encoder_fwd(const float* mix, const float* U, int M, int T, int N, int L
 int run_encoder_bwd(const float* mix, const float* w, const float* dwa, const float* dwb, int M, int T, int N, int L,
                     float* dU, cudaStream_t s) {
   const int S = L / 2, K = (T - L) / S + 1;
-  const size_t smem = (size_t)(L * N + ENCB_TK * S + L) * sizeof(float);
+  CTN_REQUIRE(L <= ENC_MAXL, "encoder: L <= %d supported (got %d)", ENC_MAXL, L);
+  const size_t smem = (size_t)(ENCB_TK * S + L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)encoder_bwd_kernel, smem));
   encoder_bwd_kernel<<<dim3(cdiv(K, ENCB_TK), M), 256, smem, s>>>(mix, w, dwa, dwb, T, K, N, L, dU);
   return check_launch("encoder_bwd_kernel");
@@ -852,7 +888,8 @@ int run_decoder_fwd(const float* score, const float* w, const float* V, int M, i
                     int softmax, float* est, cudaStream_t s) {
   CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
   const int S = L / 2, halo = (L - 1) / S;
-  const size_t smem = (size_t)(L * (N + 1) + (DEC_TK + halo) * C * L + 8 * C * N) * sizeof(float);
+  CTN_REQUIRE(N <= 32 * DEC_MAXN, "decoder: N <= %d supported (got %d)", 32 * DEC_MAXN, N);
+  const size_t smem = (size_t)(L * N + (DEC_TK + halo) * C * L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)decoder_fwd_kernel, smem));
   decoder_fwd_kernel<<<dim3(cdiv(K, DEC_TK), M), 256, smem, s>>>(score, w, V, K, C, N, L, T, softmax, est);
   return check_launch("decoder_fwd_kernel");
@@ -861,7 +898,8 @@ int run_decoder_fwd(const float* score, const float* w, const float* V, int M, i
 int run_decoder_bwd(const float* d_est, const float* score, const float* w, const float* V, int M, int K, int C, int N,
                     int L, int T, int softmax, float* d_score, float* d_w, float* dV, cudaStream_t s) {
   CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
-  const size_t smem = (size_t)(2 * L * N + DECB_TK * C * L) * sizeof(float);
+  CTN_REQUIRE(L <= DEC_MAXL, "decoder: L <= %d supported (got %d)", DEC_MAXL, L);
+  const size_t smem = (size_t)(DECB_TK * C * L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)decoder_bwd_kernel, smem));
   decoder_bwd_kernel<<<dim3(cdiv(K, DECB_TK), M), 256, smem, s>>>(d_est, score, w, V, K, C, N, L, T, softmax, d_score,
                                                                  d_w, dV);

@@ -9,7 +9,7 @@ namespace {
 constexpr int PIT_MAXC = 4;
 constexpr int PIT_NMOM = 4 * PIT_MAXC + PIT_MAXC * PIT_MAXC + PIT_MAXC;  // Se, See, Ss_all, Ss, Sss, Ses
 constexpr int PIT_THREADS = 256;
-constexpr int PIT_PER_THREAD = 16;
+constexpr int PIT_PER_THREAD = 4;
 
 // moment slots for sample b (doubles):
 //   [0,C)        Se[i]    masked sum of est
