@@ -42,6 +42,31 @@ int lib_scratch(size_t bytes, void** out, int slot);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// pdl_launch_dependents() (lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs are resident,
+// e.g. on the SMs the last partial wave leaves idle) and pdl_wait() (blocks until the PREVIOUS kernel has completed and
+// its writes are visible) before it touches any global data.  CTN_NO_PDL=1 disables the launch attribute (A/B).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors are picked up by check_launch()
+}
+
 // ---- normalisation statistics -----------------------------------------------------------
 // gLN: per-sample (sum, sumsq) accumulated in fp64 by the producing kernel; consumers derive
 //      mean / rstd on the fly (no finalize kernel).  cLN: per-frame (mean, rstd) floats.

@@ -21,6 +21,8 @@ __device__ __forceinline__ float dprelu(float z, float a) { return z > 0.f ? 1.f
 constexpr int ENC_TK = 16;
 __global__ void __launch_bounds__(256) encoder_fwd_kernel(const float* __restrict__ mix, const float* __restrict__ U,
                                                           int T, int K, int N, int L, float* __restrict__ w) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* Ut = sm;           // [L][N]
   float* xs = sm + L * N;   // [ENC_TK*S + L]
@@ -48,6 +50,8 @@ constexpr int ENC_MAXL = 32;
 __global__ void __launch_bounds__(256) encoder_bwd_kernel(const float* __restrict__ mix, const float* __restrict__ w,
                                                           const float* __restrict__ dwa, const float* __restrict__ dwb,
                                                           int T, int K, int N, int L, float* __restrict__ dU) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* xs = sm;  // [ENCB_TK*S + L]
   const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENCB_TK;
@@ -79,6 +83,8 @@ __global__ void __launch_bounds__(256) encoder_bwd_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
                                                         int64_t F, int Ch, float* __restrict__ rowstat) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= F) return;
@@ -115,6 +121,8 @@ __global__ void __launch_bounds__(256) prep_normfold_kernel(const float* __restr
                                                             int64_t in_stride, float* __restrict__ Wg,
                                                             float* __restrict__ c1, float* __restrict__ c2,
                                                             int64_t wg_stride, int64_t c_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
@@ -163,6 +171,8 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
                                                          int K, int H, int P, int dil, int cshift,
                                                          float* __restrict__ z2, double* __restrict__ stat_out,
                                                          const float* __restrict__ alpha2) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
   const int m = blockIdx.y;
@@ -267,6 +277,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ Wd, int K, int H, int P, int dil,
                                                          int cshift, float* __restrict__ dn1, float* __restrict__ part,
                                                          double* __restrict__ red1) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
   const int m = blockIdx.y;
@@ -376,6 +388,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nb, int H, int P,
                                                               float* __restrict__ dW, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = (P + 2) * H;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -406,6 +420,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
                                                               const float* __restrict__ alpha, NormStats st,
                                                               const float* __restrict__ gamma, int K, int Ch,
                                                               float* __restrict__ part, double* __restrict__ redout) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[2 * 32];
   __shared__ float2 s_st;
   const int m = blockIdx.y, k0 = blockIdx.x * NR_TK;
@@ -473,6 +489,8 @@ __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ 
                                                             const float* __restrict__ alpha, NormStats st,
                                                             const float* __restrict__ gamma, const double* __restrict__ redin,
                                                             int K, int Ch, float* __restrict__ dalpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[32];
   __shared__ float4 s_st;
   const int m = blockIdx.y, k0 = blockIdx.x * GA_TK;
@@ -533,6 +551,8 @@ __global__ void __launch_bounds__(256) cln_bwd_apply_kernel(float* __restrict__ 
                                                             const float* __restrict__ alpha, const float* __restrict__ rowstat,
                                                             const float* __restrict__ gamma, int64_t F, int Ch,
                                                             float* __restrict__ dalpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -586,6 +606,8 @@ constexpr int DEC_MAXN = 16;  // per-lane basis channels (N <= 512)
 __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ score, const float* __restrict__ w,
                                                           const float* __restrict__ V, int K, int C, int N, int L,
                                                           int T, int softmax, float* __restrict__ est) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int S = L / 2;
   const int halo = (L - 1) / S;  // frames before the tile that still reach into it
@@ -666,6 +688,8 @@ __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restric
                                                           int C, int N, int L, int T, int softmax,
                                                           float* __restrict__ d_score, float* __restrict__ d_w,
                                                           float* __restrict__ dV) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int S = L / 2;
   float* df = sm;  // [DECB_TK][C][L]
@@ -745,6 +769,8 @@ __global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restric
 // utils.overlap_and_add as a standalone op: out[o, t] = sum_k sig[o, k, t - k*step], ascending k
 __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ sig, int frames, int flen, int step,
                                                   int64_t out_len, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t o = blockIdx.y;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= out_len) return;
@@ -779,7 +805,7 @@ int run_encoder_fwd(const float* mix, const float* U, int M, int T, int N, int L
   const int S = L / 2, K = (T - L) / S + 1;
   const size_t smem = (size_t)(L * N + ENC_TK * S + L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)encoder_fwd_kernel, smem));
-  encoder_fwd_kernel<<<dim3(cdiv(K, ENC_TK), M), 256, smem, s>>>(mix, U, T, K, N, L, w);
+  launch_kernel(encoder_fwd_kernel, dim3(cdiv(K, ENC_TK), M), 256, smem, s, mix, U, T, K, N, L, w);
   return check_launch("encoder_fwd_kernel");
 }
 
@@ -789,20 +815,19 @@ int run_encoder_bwd(const float* mix, const float* w, const float* dwa, const fl
   CTN_REQUIRE(L <= ENC_MAXL, "encoder: L <= %d supported (got %d)", ENC_MAXL, L);
   const size_t smem = (size_t)(ENCB_TK * S + L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)encoder_bwd_kernel, smem));
-  encoder_bwd_kernel<<<dim3(cdiv(K, ENCB_TK), M), 256, smem, s>>>(mix, w, dwa, dwb, T, K, N, L, dU);
+  launch_kernel(encoder_bwd_kernel, dim3(cdiv(K, ENCB_TK), M), 256, smem, s, mix, w, dwa, dwb, T, K, N, L, dU);
   return check_launch("encoder_bwd_kernel");
 }
 
 int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s) {
   CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
-  row_stats_kernel<<<cdiv(F, 8), 256, 0, s>>>(x, alpha, F, Ch, rowstat);
+  launch_kernel(row_stats_kernel, cdiv(F, 8), 256, 0, s, x, alpha, F, Ch, rowstat);
   return check_launch("row_stats_kernel");
 }
 
 int run_prep_normfold(const float* W, const float* gamma, const float* beta, int O, int I, int nb, int64_t in_stride,
                       float* Wg, float* c1, float* c2, int64_t wg_stride, int64_t c_stride, cudaStream_t s) {
-  prep_normfold_kernel<<<dim3(cdiv(O, 8), nb), 256, 0, s>>>(W, gamma, beta, O, I, in_stride, Wg, c1, c2, wg_stride,
-                                                            c_stride);
+  launch_kernel(prep_normfold_kernel, dim3(cdiv(O, 8), nb), 256, 0, s, W, gamma, beta, O, I, in_stride, Wg, c1, c2, wg_stride, c_stride);
   return check_launch("prep_normfold_kernel");
 }
 
@@ -815,11 +840,9 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
   const int cshift = causal ? P - 1 : (P - 1) / 2;
   const dim3 grid(dw_blocks(K, dil), M);
   if (P == 3)
-    dwconv_fwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift,
-                                                               z2, stat_out, alpha2);
+    launch_kernel(dwconv_fwd_kernel<3>, grid, block_for_channels(H), 0, s, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, z2, stat_out, alpha2);
   else
-    dwconv_fwd_kernel<0><<<grid, block_for_channels(H), 0, s>>>(z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift,
-                                                               z2, stat_out, alpha2);
+    launch_kernel(dwconv_fwd_kernel<0>, grid, block_for_channels(H), 0, s, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, z2, stat_out, alpha2);
   return check_launch("dwconv_fwd_kernel");
 }
 
@@ -827,7 +850,7 @@ static int fold_partials(const float* part, int nb, int H, int P, float* dW, flo
                          cudaStream_t s) {
   int splits = nb / 32;
   splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
-  reduce_partials_kernel<<<dim3(cdiv((int64_t)(P + 2) * H, 256), splits), 256, 0, s>>>(part, nb, H, P, dW, dgamma, dbeta);
+  launch_kernel(reduce_partials_kernel, dim3(cdiv((int64_t)(P + 2) * H, 256), splits), 256, 0, s, part, nb, H, P, dW, dgamma, dbeta);
   return check_launch("reduce_partials_kernel");
 }
 
@@ -848,11 +871,9 @@ int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormS
   const int cshift = causal ? P - 1 : (P - 1) / 2;
   const dim3 grid(dw_blocks(K, dil), M);
   if (P == 3)
-    dwconv_bwd_kernel<3><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
-                                                               cshift, dn1, part, red1);
+    launch_kernel(dwconv_bwd_kernel<3>, grid, block_for_channels(H), 0, s, dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
   else
-    dwconv_bwd_kernel<0><<<grid, block_for_channels(H), 0, s>>>(dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil,
-                                                               cshift, dn1, part, red1);
+    launch_kernel(dwconv_bwd_kernel<0>, grid, block_for_channels(H), 0, s, dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
   CTN_TRY(check_launch("dwconv_bwd_kernel"));
   return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);
 }
@@ -866,7 +887,7 @@ int run_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, Nor
     part = reinterpret_cast<float*>(scr);
   }
   const dim3 grid(cdiv(K, NR_TK), M);
-  norm_bwd_reduce_kernel<<<grid, block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, K, Ch, part, red);
+  launch_kernel(norm_bwd_reduce_kernel, grid, block_for_channels(Ch), 0, s, dn, z, alpha, st, gamma, K, Ch, part, red);
   CTN_TRY(check_launch("norm_bwd_reduce_kernel"));
   return fold_partials(part, grid.x * grid.y, Ch, 0, nullptr, dgamma, dbeta, s);
 }
@@ -875,12 +896,10 @@ int run_norm_bwd_apply(float* dn, const float* z, const float* alpha, NormStats 
                        const double* red, int M, int K, int Ch, float* dalpha, cudaStream_t s) {
   CTN_REQUIRE(Ch % 4 == 0, "norm_bwd: channels must be a multiple of 4 (got %d)", Ch);
   if (st.row != nullptr) {
-    cln_bwd_apply_kernel<<<cdiv((int64_t)M * K, 8), 256, 0, s>>>(dn, z, alpha, st.row, gamma, (int64_t)M * K, Ch,
-                                                               dalpha);
+    launch_kernel(cln_bwd_apply_kernel, cdiv((int64_t)M * K, 8), 256, 0, s, dn, z, alpha, st.row, gamma, (int64_t)M * K, Ch, dalpha);
     return check_launch("cln_bwd_apply_kernel");
   }
-  gln_bwd_apply_kernel<<<dim3(cdiv(K, GA_TK), M), block_for_channels(Ch), 0, s>>>(dn, z, alpha, st, gamma, red, K, Ch,
-                                                                                 dalpha);
+  launch_kernel(gln_bwd_apply_kernel, dim3(cdiv(K, GA_TK), M), block_for_channels(Ch), 0, s, dn, z, alpha, st, gamma, red, K, Ch, dalpha);
   return check_launch("gln_bwd_apply_kernel");
 }
 
@@ -891,7 +910,7 @@ int run_decoder_fwd(const float* score, const float* w, const float* V, int M, i
   CTN_REQUIRE(N <= 32 * DEC_MAXN, "decoder: N <= %d supported (got %d)", 32 * DEC_MAXN, N);
   const size_t smem = (size_t)(L * N + (DEC_TK + halo) * C * L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)decoder_fwd_kernel, smem));
-  decoder_fwd_kernel<<<dim3(cdiv(K, DEC_TK), M), 256, smem, s>>>(score, w, V, K, C, N, L, T, softmax, est);
+  launch_kernel(decoder_fwd_kernel, dim3(cdiv(K, DEC_TK), M), 256, smem, s, score, w, V, K, C, N, L, T, softmax, est);
   return check_launch("decoder_fwd_kernel");
 }
 
@@ -901,8 +920,7 @@ int run_decoder_bwd(const float* d_est, const float* score, const float* w, cons
   CTN_REQUIRE(L <= DEC_MAXL, "decoder: L <= %d supported (got %d)", DEC_MAXL, L);
   const size_t smem = (size_t)(DECB_TK * C * L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)decoder_bwd_kernel, smem));
-  decoder_bwd_kernel<<<dim3(cdiv(K, DECB_TK), M), 256, smem, s>>>(d_est, score, w, V, K, C, N, L, T, softmax, d_score,
-                                                                 d_w, dV);
+  launch_kernel(decoder_bwd_kernel, dim3(cdiv(K, DECB_TK), M), 256, smem, s, d_est, score, w, V, K, C, N, L, T, softmax, d_score, d_w, dV);
   return check_launch("decoder_bwd_kernel");
 }
 
@@ -910,7 +928,7 @@ int run_overlap_and_add(const float* sig, int64_t outer, int frames, int flen, i
   CTN_REQUIRE(step >= 1 && step <= flen, "overlap_and_add: frame_step must be in [1, frame_length]");
   CTN_REQUIRE(outer <= 65535, "overlap_and_add: too many outer rows (%lld)", (long long)outer);
   const int64_t out_len = (int64_t)(frames - 1) * step + flen;
-  ola_kernel<<<dim3(cdiv(out_len, 256), (unsigned)outer), 256, 0, s>>>(sig, frames, flen, step, out_len, out);
+  launch_kernel(ola_kernel, dim3(cdiv(out_len, 256), (unsigned)outer), 256, 0, s, sig, frames, flen, step, out_len, out);
   return check_launch("ola_kernel");
 }
 

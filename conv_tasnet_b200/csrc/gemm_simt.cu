@@ -47,6 +47,8 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 // ------------------------------------------------------------------------------------------
 template <bool W_IS_KN>
 __global__ void __launch_bounds__(NT, 2) gemm_kernel(GemmArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   __shared__ float rowsum[BM][2];
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(GemmArgs a) {
 // dW[O,I] += sum_{f in chunk} G[f,o] * act(f,i)       (split over f, fp32 atomics)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 2) wgrad_kernel(WgradArgs a, int f_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   __shared__ StatCache sc;
@@ -317,9 +321,9 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t s) {
   CTN_REQUIRE(a.F > 0 && a.K > 0, "conv1x1: empty input (F=%lld K=%d)", (long long)a.F, a.K);
   dim3 grid(cdiv(a.F, BM), cdiv(a.O, BN));
   if (a.w_is_kn)
-    gemm_kernel<true><<<grid, NT, 0, s>>>(a);
+    launch_kernel(gemm_kernel<true>, grid, NT, 0, s, a);
   else
-    gemm_kernel<false><<<grid, NT, 0, s>>>(a);
+    launch_kernel(gemm_kernel<false>, grid, NT, 0, s, a);
   return check_launch("gemm_kernel");
 }
 
@@ -333,7 +337,7 @@ int launch_wgrad_simt(const WgradArgs& a, cudaStream_t s) {
   if (f_chunk < 4 * BK) f_chunk = 4 * BK;
   splits = cdiv(a.F, f_chunk);
   dim3 grid(cdiv(a.O, BM), cdiv(a.I, BN), splits);
-  wgrad_kernel<<<grid, NT, 0, s>>>(a, f_chunk);
+  launch_kernel(wgrad_kernel, grid, NT, 0, s, a, f_chunk);
   return check_launch("wgrad_kernel");
 }
 

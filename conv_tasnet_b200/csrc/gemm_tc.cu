@@ -272,6 +272,7 @@ template <bool TF32, bool FOLD, bool RES, bool STATS, bool NRED = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_a, TcGemmArgs a) {
+  pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int NF = a.NF, NST = a.stages, RST = a.raw_stages;
   const int a_plane = NF * 128;
@@ -314,6 +315,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global data is touched only below
   if (threadIdx.x == 0) TR(1);
   // TMEM accumulators (NF fp32 columns each).  The tensor core truncates (round-toward-zero) when it adds into its
   // fp32 accumulator, a coherent bias that grows with the length of the accumulation chain (measured: 2.7e-6 over a
@@ -644,6 +646,7 @@ struct TcWgradArgs {
 
 template <int NI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
+  pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   constexpr int A_PLANE = WK * BM * 2;   // 8 KB   (2 groups of 64 o-columns x 32 rows x 128 B)
@@ -677,6 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global data is touched only below
 
   if (nkb > 0) {
     if (warp == 1) {
@@ -805,6 +809,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int R, int C, int64_t src_stride,
                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                            int64_t dst_stride, int transpose) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const float* s = src + (int64_t)blockIdx.z * src_stride;
   __nv_bfloat16* h = hi + (int64_t)blockIdx.z * dst_stride;
@@ -840,6 +846,8 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 __global__ void __launch_bounds__(256) split_planes_tf32_kernel(const float* __restrict__ src, int64_t n, int64_t src_stride,
                                                                 float* __restrict__ hi, float* __restrict__ lo,
                                                                 int64_t dst_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float* s = src + (int64_t)blockIdx.y * src_stride;
   float* h = hi + (int64_t)blockIdx.y * dst_stride;
   float* l = lo + (int64_t)blockIdx.y * dst_stride;
@@ -974,7 +982,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
                                     227 * 1024));                                                                \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    tc_gemm_kernel<__VA_ARGS__><<<grid, TC_THREADS, smem, s>>>(mh, ml, ma, a);                                   \
+    launch_kernel(tc_gemm_kernel<__VA_ARGS__>, grid, TC_THREADS, smem, s, mh, ml, ma, a);                                   \
   } while (0)
   if (tf32) {  // forward 1x1 convs
     if (!fold && !res && !stats) CTN_TC_LAUNCH(true, false, false, false);
@@ -1019,10 +1027,10 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
   }
   if (ni == 256) {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128;
-    tc_wgrad_kernel<256><<<grid, TC_THREADS, smem, s>>>(a);
+    launch_kernel(tc_wgrad_kernel<256>, grid, TC_THREADS, smem, s, a);
   } else {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128;
-    tc_wgrad_kernel<128><<<grid, TC_THREADS, smem, s>>>(a);
+    launch_kernel(tc_wgrad_kernel<128>, grid, TC_THREADS, smem, s, a);
   }
   return check_launch("tc_wgrad_kernel");
 }
@@ -1030,16 +1038,14 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
 int run_split_planes_tf32(const float* src, int64_t n, int nb, int64_t src_stride, void* hi, void* lo,
                           int64_t dst_stride, cudaStream_t s) {
   int gx = cdiv(n, 256 * 4);
-  split_planes_tf32_kernel<<<dim3(gx < 1 ? 1 : gx, nb), 256, 0, s>>>(src, n, src_stride, reinterpret_cast<float*>(hi),
-                                                                     reinterpret_cast<float*>(lo), dst_stride);
+  launch_kernel(split_planes_tf32_kernel, dim3(gx < 1 ? 1 : gx, nb), 256, 0, s, src, n, src_stride, reinterpret_cast<float*>(hi), reinterpret_cast<float*>(lo), dst_stride);
   return check_launch("split_planes_tf32_kernel");
 }
 
 int run_split_planes(const float* src, int R, int C, int nb, int64_t src_stride, void* hi, void* lo, int64_t dst_stride,
                      int transpose, cudaStream_t s) {
   dim3 grid(cdiv(C, 32), cdiv(R, 32), nb);
-  split_planes_kernel<<<grid, 256, 0, s>>>(src, R, C, src_stride, reinterpret_cast<__nv_bfloat16*>(hi),
-                                           reinterpret_cast<__nv_bfloat16*>(lo), dst_stride, transpose);
+  launch_kernel(split_planes_kernel, grid, 256, 0, s, src, R, C, src_stride, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), dst_stride, transpose);
   return check_launch("split_planes_kernel");
 }
 

@@ -19,6 +19,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTN_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 static unsigned long long g_launches = 0;  // kernels launched through this library (bench.py's gpu_launches)
 int check_launch(const char* what) {
   __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);

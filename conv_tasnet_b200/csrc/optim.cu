@@ -10,6 +10,8 @@ constexpr int RB = 512;  // reduction blocks
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ part,
                                                     unsigned int* __restrict__ ticket, float max_norm,
                                                     float* __restrict__ norm_out, float* __restrict__ scale_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   __shared__ bool is_last;
   double acc[1] = {0.0};
@@ -46,6 +48,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sc = __ldg(scale);
   if (sc == 1.f) return;
   const int64_t n4 = n / 4;
@@ -58,11 +62,15 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ g, int64
     for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) g[i] *= sc;
 }
 
-__global__ void step_inc_kernel(int64_t* step) { step[0] += 1; }
+__global__ void step_inc_kernel(int64_t* step) {
+  pdl_launch_dependents();
+  pdl_wait(); step[0] += 1; }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                                    float wd, const int64_t* __restrict__ step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double t = (double)step[0];
   const float bias1 = (float)(1.0 - pow((double)b1, t));
   const float bias2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
@@ -88,17 +96,17 @@ int run_clip_grad_norm(float* grads, int64_t n, float max_norm, float* norm_out,
   unsigned int* ticket = reinterpret_cast<unsigned int*>(part + RB);
   float* scale = reinterpret_cast<float*>(ticket + 2);
   CTN_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
-  sumsq_kernel<<<RB, 256, 0, s>>>(grads, n, part, ticket, max_norm, norm_out, scale);
+  launch_kernel(sumsq_kernel, RB, 256, 0, s, grads, n, part, ticket, max_norm, norm_out, scale);
   CTN_TRY(check_launch("sumsq_kernel"));
-  scale_kernel<<<592, 256, 0, s>>>(grads, n, scale);
+  launch_kernel(scale_kernel, 592, 256, 0, s, grads, n, scale);
   return check_launch("scale_kernel");
 }
 
 int run_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                   float wd, int64_t* step_dev, cudaStream_t s) {
-  step_inc_kernel<<<1, 1, 0, s>>>(step_dev);
+  launch_kernel(step_inc_kernel, 1, 1, 0, s, step_dev);
   CTN_TRY(check_launch("step_inc_kernel"));
-  adam_kernel<<<1184, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev);
+  launch_kernel(adam_kernel, 1184, 256, 0, s, p, g, m, v, n, lr, b1, b2, eps, wd, step_dev);
   return check_launch("adam_kernel");
 }
 

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(PIT_THREADS) pit_moments_kernel(const float* _
                                                                   int T, PitWs ws, float* __restrict__ loss,
                                                                   float* __restrict__ max_snr, int64_t* __restrict__ idx_out,
                                                                   float* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double scratch[32];
   __shared__ bool is_last;
   const int b = blockIdx.y;
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(256) pit_bwd_kernel(const float* __restrict__ 
                                                       const int64_t* __restrict__ lengths, const float* __restrict__ coef,
                                                       const float* __restrict__ grad_loss, int C, int T,
                                                       float* __restrict__ d_est) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bc = blockIdx.y, b = bc / C;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -201,6 +205,8 @@ __global__ void __launch_bounds__(256) pit_bwd_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                                       int C, int64_t inner, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bc = blockIdx.y, b = bc / C, c = bc - b * C;
   int perm[PIT_MAXC];
   unrank_perm((int)idx[b], C, perm);
@@ -227,11 +233,11 @@ int run_pit_forward(const float* source, float* est, const int64_t* lengths, int
   ws.ticket = reinterpret_cast<unsigned int*>(ws.mom + (int64_t)B * PIT_NMOM);
   ws.done = ws.ticket + B;
   const int chunks = cdiv(T, PIT_THREADS * PIT_PER_THREAD);
-  pit_moments_kernel<<<dim3(chunks, B), PIT_THREADS, 0, s>>>(source, est, lengths, B, C, T, ws, loss, max_snr, idx, coef);
+  launch_kernel(pit_moments_kernel, dim3(chunks, B), PIT_THREADS, 0, s, source, est, lengths, B, C, T, ws, loss, max_snr, idx, coef);
   CTN_TRY(check_launch("pit_moments_kernel"));
   if (reorder != nullptr) {
     int gx = cdiv(T, 256 * 8);
-    reorder_kernel<<<dim3(gx < 1 ? 1 : gx, B * C), 256, 0, s>>>(est, idx, C, T, reorder);
+    launch_kernel(reorder_kernel, dim3(gx < 1 ? 1 : gx, B * C), 256, 0, s, est, idx, C, T, reorder);
     CTN_TRY(check_launch("reorder_kernel"));
   }
   return 0;
@@ -240,14 +246,14 @@ int run_pit_forward(const float* source, float* est, const int64_t* lengths, int
 int run_pit_backward(const float* source, const float* est_masked, const int64_t* lengths, const float* coef,
                      const float* grad_loss, int B, int C, int T, float* d_est, cudaStream_t s) {
   CTN_REQUIRE(C >= 1 && C <= PIT_MAXC && B * C <= 65535, "PIT backward: bad shape");
-  pit_bwd_kernel<<<dim3(cdiv(T, 256), B * C), 256, 0, s>>>(source, est_masked, lengths, coef, grad_loss, C, T, d_est);
+  launch_kernel(pit_bwd_kernel, dim3(cdiv(T, 256), B * C), 256, 0, s, source, est_masked, lengths, coef, grad_loss, C, T, d_est);
   return check_launch("pit_bwd_kernel");
 }
 
 int run_reorder(const float* source, const int64_t* idx, int B, int C, int64_t inner, float* out, cudaStream_t s) {
   CTN_REQUIRE(C >= 1 && C <= PIT_MAXC && B * C <= 65535, "reorder_source: bad shape");
   int gx = cdiv(inner, 256 * 8);
-  reorder_kernel<<<dim3(gx < 1 ? 1 : gx, B * C), 256, 0, s>>>(source, idx, C, inner, out);
+  launch_kernel(reorder_kernel, dim3(gx < 1 ? 1 : gx, B * C), 256, 0, s, source, idx, C, inner, out);
   return check_launch("reorder_kernel");
 }
 
