@@ -299,40 +299,42 @@ def main():
         secs_fwd = timed(lambda: infer(mix_d), args.steps)
     model.train()
 
-    # ---- roofline of the dominant kernel: the 1x1-conv GEMM at its most frequent shape (B->H, F frames) --
+    # ---- roofline of the dominant kernel by time share (profiles/r1_final_summary.md): the weight-gradient GEMM
+    # dW[H,B] = dz1[F,H]^T x[F,B] on tcgen05 (bf16x3 split, MN-major operands), timed live on its own launches --------
     pk, pk_src = peaks()
     K = L.ctn_num_frames(ctypes.byref(model._cfg), T)
     F = M * K
-    A = torch.randn(F, PAPER["B"], device=dev)
-    W = torch.randn(PAPER["H"], PAPER["B"], device=dev) * 0.05
-    D = torch.empty(F, PAPER["H"], device=dev)
+    Gm = torch.randn(F, PAPER["H"], device=dev)
+    Xm = torch.randn(F, PAPER["B"], device=dev)
+    dWm = torch.zeros(PAPER["H"], PAPER["B"], device=dev)
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)  # >> L2 (126 MB); also keeps the GPU busy while the
     # host enqueues the timed launch, so the event pair brackets the kernel alone and not host launch latency
     st = _lib.stream()
 
-    def gemm():
-        _lib.check(L.ctn_conv1x1(A.data_ptr(), W.data_ptr(), 0, D.data_ptr(), F, PAPER["H"], PAPER["B"], K, None, None,
-                                 None, None, None, None, None, None, st))
+    def wgrad():
+        _lib.check(L.ctn_wgrad(Gm.data_ptr(), Xm.data_ptr(), dWm.data_ptr(), F, PAPER["H"], PAPER["B"], K, None, None,
+                               None, None, None, st))
     for _ in range(3):
-        gemm()
+        wgrad()
     reps, tot = 10, 0.0
     for _ in range(reps):
         flush.zero_()  # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        gemm()
+        wgrad()
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1) * 1e-3
-    t_gemm = tot / reps
+    t_k = tot / reps
     flops = 2.0 * F * PAPER["B"] * PAPER["H"]
-    ach = flops / t_gemm / 1e12
-    roofline = {"kernel": "tc_gemm_kernel<TF32> forward 1x1 conv B->H (tcgen05, TF32x3 split, TMEM accumulators)",
-                "bound": "tensor", "achieved": ach,
-                "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
-                "peak_source": pk_src + ", bf16 burst (TF32x3 issues 3 tf32 MMAs per algorithmic MAC = 6 bf16-equivalents, "
-                "so the ceiling of this fraction is 1/6)", "launch_us": t_gemm * 1e6, "alg_flops_per_launch": flops,
-                "includes": "weight split kernel of the standalone entry point (~2 us)"}
+    ach = flops / t_k / 1e12
+    roofline = {"kernel": "tc_wgrad_kernel<256>: dW[512,256] = dz1[F,512]^T x[F,256] (tcgen05, bf16x3 split, MN-major "
+                "operands, split-K + red.v4), 22.9 % of the step", "bound": "tensor", "achieved": ach,
+                "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                "traffic": 30054912, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per "
+                "launch (profiles/r1_final_wgrad_full_raw.csv); algorithmic input 29.5 MB",
+                "peak_source": pk_src + ", bf16 burst (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the "
+                "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops}
 
     # whole-step algorithmic rates (SURVEY §8d per-frame figures x frames)
     frames = world * F

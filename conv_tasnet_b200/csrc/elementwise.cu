@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256) cln_bwd_apply_kernel(float* __restrict__ 
 // grid (frame tiles, M); one warp per frame computes frames[k][c][l]; then the block writes its
 // span of output samples (each sample sums the <= ceil(L/S) frames that cover it, ascending k).
 // ---------------------------------------------------------------------------------------
-constexpr int DEC_TK = 8;
+constexpr int DEC_TK = 16;
 constexpr int MAXC = 4;
 constexpr int DEC_MAXN = 16;  // per-lane basis channels (N <= 512)
 __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ score, const float* __restrict__ w,
@@ -621,8 +621,14 @@ __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restric
   for (int k = kb + wid; k < ke; k += nw) {  // one frame per warp: lanes own n = lane + 32 i
     const int64_t f = (int64_t)m * K + k;
     float sw[MAXC][DEC_MAXN];
+    const int ni = (N + 31) >> 5;  // per-lane channels actually present
 #pragma unroll
     for (int i = 0; i < DEC_MAXN; ++i) {
+      if (i >= ni) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) sw[c][i] = 0.f;
+        continue;
+      }
       const int n = lane + 32 * i;
       float sc[MAXC];
       const float wv = n < N ? w[f * N + n] : 0.f;
@@ -648,6 +654,7 @@ __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restric
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < DEC_MAXN; ++i) {
+          if (i >= ni) break;
           const int n = lane + 32 * i;
           float swv = sw[0][i];
 #pragma unroll
