@@ -28,7 +28,7 @@
 namespace ctn {
 #ifdef CTN_TRACE
 __device__ long long g_trace[512][64];
-#define TR(slot) do { g_trace[blockIdx.y * gridDim.x + blockIdx.x][slot] = clock64(); } while (0)
+#define TR(slot) do { g_trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 511][slot] = clock64(); } while (0)
 #else
 #define TR(slot) do { } while (0)
 #endif
