@@ -795,7 +795,7 @@ static int block_for_channels(int Ch) {
 }
 
 static int ensure_smem(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 48 * 1024) {  // (set on every such launch: the attribute is per device and these launches are rare)
     CTN_REQUIRE(bytes <= 227 * 1024, "kernel needs %zu bytes of shared memory (> 227 KB): N*L too large", bytes);
     CTN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   }

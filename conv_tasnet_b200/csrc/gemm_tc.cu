@@ -976,11 +976,13 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
 #define CTN_TC_LAUNCH(...)                                                                                       \
   do {                                                                                                           \
-    static bool attr_set = false;                                                                                \
-    if (!attr_set) {                                                                                             \
+    static unsigned long long attr_mask = 0;  /* the attribute is per device */                                  \
+    int dev__ = 0;                                                                                               \
+    CTN_CUDA(cudaGetDevice(&dev__));                                                                             \
+    if (!((attr_mask >> (dev__ & 63)) & 1ull)) {                                                                 \
       CTN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                     227 * 1024));                                                                \
-      attr_set = true;                                                                                           \
+      attr_mask |= 1ull << (dev__ & 63);                                                                         \
     }                                                                                                            \
     launch_kernel(tc_gemm_kernel<__VA_ARGS__>, grid, TC_THREADS, smem, s, mh, ml, ma, a);                                   \
   } while (0)
@@ -1019,11 +1021,13 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
   splits = cdiv(w.F, f_chunk);
   a.f_chunk = f_chunk;
   dim3 grid(w.O / BM, w.I / ni, splits);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // the attribute is per device
+  int dev = 0;
+  CTN_CUDA(cudaGetDevice(&dev));
+  if (!((attr_mask >> (dev & 63)) & 1ull)) {
     CTN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CTN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_mask |= 1ull << (dev & 63);
   }
   if (ni == 256) {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128;

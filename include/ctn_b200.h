@@ -56,7 +56,9 @@ int64_t ctn_workspace_bytes(const ctn_config* cfg, int32_t M, int32_t T, int32_t
 
 /* ---- whole-path entry points ------------------------------------------------------------ */
 /* ConvTasNet.forward (src/conv_tasnet.py:45-60): mixture [M,T] -> est [M,C,T] (right zero-padded).
- * training != 0 additionally leaves the stash in `workspace` for ctn_model_backward. */
+ * training != 0 additionally leaves the stash in `workspace` for ctn_model_backward and runs the 1x1 convs with the
+ * TF32x3 operand split (fp32-class forward: needed for gradient parity); training == 0 uses the bf16x3
+ * split (outputs within 2e-5 of the training path, budget 1e-4). */
 int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const float* mixture,
                           int32_t M, int32_t T, float* est, void* workspace, int64_t workspace_bytes,
                           int32_t training, cudaStream_t stream);
