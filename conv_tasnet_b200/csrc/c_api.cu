@@ -11,9 +11,9 @@ int run_prep_normfold(const float*, const float*, const float*, int, int, int, i
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
                    int, int, float*, double*, const float*, cudaStream_t);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
-                   int, int, int, int, int, float*, float*, float*, float*, double*, float*, cudaStream_t);
+                   int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
-                        float*, double*, float*, cudaStream_t);
+                        float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
                        float*, cudaStream_t);
 int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
@@ -138,14 +138,14 @@ int32_t ctn_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, c
                        int32_t K, int32_t H, int32_t P, int32_t dilation, int32_t causal, float* dn1, float* dWd,
                        float* dgamma1, float* dbeta1, double* red1, cudaStream_t stream) {
   return run_dwconv_bwd(dz2, z1, alpha1, make_stats(gln_acc1, rowstat1, K, H), gamma1, beta1, Wd, M, K, H, P, dilation,
-                        causal, dn1, dWd, dgamma1, dbeta1, red1, nullptr, stream);
+                        causal, dn1, dWd, dgamma1, dbeta1, red1, nullptr, 0, stream);
 }
 
 int32_t ctn_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, const double* gln_acc,
                             const float* rowstat, const float* gamma, int32_t M, int32_t K, int32_t Ch, float* dgamma,
                             float* dbeta, double* red, cudaStream_t stream) {
   return run_norm_bwd_reduce(dn, z, alpha, make_stats(gln_acc, rowstat, K, Ch), gamma, M, K, Ch, dgamma, dbeta, red,
-                             nullptr, stream);
+                             nullptr, 0, stream);
 }
 
 int32_t ctn_norm_bwd_apply(float* dn, const float* z, const float* alpha, const double* gln_acc, const float* rowstat,

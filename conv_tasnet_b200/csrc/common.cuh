@@ -125,6 +125,19 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
   }
 }
 
+// one deferred fold of per-block partial rows (see reduce_partials_kernel); up to FOLD_MAX entries per launch
+struct FoldEntry {
+  const float* part;
+  int nb, H, P;
+  float* dW;
+  float* dgamma;
+  float* dbeta;
+};
+constexpr int FOLD_MAX = 48;
+struct FoldBatch {
+  FoldEntry e[FOLD_MAX];
+};
+
 // ---- kernel launchers implemented across the .cu files (host) ---------------------------
 struct GemmArgs {
   const float* A;  // [F, Kd]

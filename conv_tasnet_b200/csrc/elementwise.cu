@@ -853,6 +853,32 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
   return check_launch("dwconv_fwd_kernel");
 }
 
+// the same fold for a batch of independent (partial rows -> gradient slots) entries in ONE launch: blockIdx.z = entry
+__global__ void __launch_bounds__(256) reduce_partials_batch_kernel(FoldBatch fb) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const FoldEntry& e = fb.e[blockIdx.z];
+  const int n = (e.P + 2) * e.H;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int per = (e.nb + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(e.nb, b0 + per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = b0;
+  for (; b + 3 < b1; b += 4) {
+    s0 += e.part[(int64_t)b * n + i];
+    s1 += e.part[(int64_t)(b + 1) * n + i];
+    s2 += e.part[(int64_t)(b + 2) * n + i];
+    s3 += e.part[(int64_t)(b + 3) * n + i];
+  }
+  for (; b < b1; ++b) s0 += e.part[(int64_t)b * n + i];
+  const float v = (s0 + s1) + (s2 + s3);
+  const int q = i / e.H, c = i - q * e.H;
+  if (q < e.P) atomicAdd(e.dW + c * e.P + q, v);
+  else if (q == e.P) atomicAdd(e.dgamma + c, v);
+  else atomicAdd(e.dbeta + c, v);
+}
+
 static int fold_partials(const float* part, int nb, int H, int P, float* dW, float* dgamma, float* dbeta,
                          cudaStream_t s) {
   int splits = nb / 32;
@@ -868,7 +894,8 @@ int64_t norm_bwd_partial_floats(int M, int K, int Ch) { return (int64_t)cdiv(K, 
 
 int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormStats st1, const float* gamma1,
                    const float* beta1, const float* Wd, int M, int K, int H, int P, int dil, int causal, float* dn1,
-                   float* dWd, float* dgamma1, float* dbeta1, double* red1, float* part, cudaStream_t s) {
+                   float* dWd, float* dgamma1, float* dbeta1, double* red1, float* part, int defer_fold,
+                   cudaStream_t s) {
   CTN_REQUIRE(H % 4 == 0 && P >= 1 && P <= MAXP, "dwconv_bwd: bad H/P (%d/%d)", H, P);
   if (part == nullptr) {  // standalone call: library-owned scratch
     void* scr = nullptr;
@@ -882,11 +909,13 @@ int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormS
   else
     launch_kernel(dwconv_bwd_kernel<0>, grid, block_for_channels(H), 0, s, dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
   CTN_TRY(check_launch("dwconv_bwd_kernel"));
+  if (defer_fold) return 0;  // the caller folds a whole stage's partial rows in one launch (run_fold_batch)
   return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);
 }
 
 int run_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, NormStats st, const float* gamma, int M,
-                        int K, int Ch, float* dgamma, float* dbeta, double* red, float* part, cudaStream_t s) {
+                        int K, int Ch, float* dgamma, float* dbeta, double* red, float* part, int defer_fold,
+                        cudaStream_t s) {
   CTN_REQUIRE(Ch % 4 == 0, "norm_bwd: channels must be a multiple of 4 (got %d)", Ch);
   if (part == nullptr) {
     void* scr = nullptr;
@@ -896,6 +925,7 @@ int run_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, Nor
   const dim3 grid(cdiv(K, NR_TK), M);
   launch_kernel(norm_bwd_reduce_kernel, grid, block_for_channels(Ch), 0, s, dn, z, alpha, st, gamma, K, Ch, part, red);
   CTN_TRY(check_launch("norm_bwd_reduce_kernel"));
+  if (defer_fold) return 0;
   return fold_partials(part, grid.x * grid.y, Ch, 0, nullptr, dgamma, dbeta, s);
 }
 
@@ -908,6 +938,23 @@ int run_norm_bwd_apply(float* dn, const float* z, const float* alpha, NormStats 
   }
   launch_kernel(gln_bwd_apply_kernel, dim3(cdiv(K, GA_TK), M), block_for_channels(Ch), 0, s, dn, z, alpha, st, gamma, red, K, Ch, dalpha);
   return check_launch("gln_bwd_apply_kernel");
+}
+
+int dwconv_bwd_blocks(int M, int K, int dil) { return dw_blocks(K, dil) * M; }
+int norm_bwd_blocks(int M, int K) { return cdiv(K, NR_TK) * M; }
+
+int run_fold_batch(const FoldBatch& fb, int n_entries, cudaStream_t s) {
+  CTN_REQUIRE(n_entries >= 1 && n_entries <= FOLD_MAX, "fold batch: %d entries", n_entries);
+  int maxn = 0, maxnb = 0;
+  for (int i = 0; i < n_entries; ++i) {
+    const int n = (fb.e[i].P + 2) * fb.e[i].H;
+    maxn = n > maxn ? n : maxn;
+    maxnb = fb.e[i].nb > maxnb ? fb.e[i].nb : maxnb;
+  }
+  int splits = maxnb / 32;
+  splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
+  launch_kernel(reduce_partials_batch_kernel, dim3(cdiv(maxn, 256), splits, n_entries), 256, 0, s, fb);
+  return check_launch("reduce_partials_batch_kernel");
 }
 
 int run_decoder_fwd(const float* score, const float* w, const float* V, int M, int K, int C, int N, int L, int T,

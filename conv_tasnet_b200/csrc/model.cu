@@ -49,11 +49,14 @@ int run_prep_normfold(const float*, const float*, const float*, int, int, int, i
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
                    int, int, float*, double*, const float*, cudaStream_t);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
-                   int, int, int, int, int, float*, float*, float*, float*, double*, float*, cudaStream_t);
+                   int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
-                        float*, double*, float*, cudaStream_t);
+                        float*, double*, float*, int, cudaStream_t);
 int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P, int dil);
 int64_t norm_bwd_partial_floats(int M, int K, int Ch);
+int dwconv_bwd_blocks(int M, int K, int dil);
+int norm_bwd_blocks(int M, int K);
+int run_fold_batch(const FoldBatch& fb, int n_entries, cudaStream_t s);
 int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
                        float*, cudaStream_t);
 int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
@@ -120,17 +123,22 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
 
 // GEMM whose output is the gradient w.r.t. a normalised activation, plus the norm-backward reduction over that output:
 // fused into the tcgen05 epilogue when the shape is on the MMA grid, otherwise GEMM followed by norm_bwd_reduce
+static bool nred_fusion_enabled() {
+  return env_flag("CTN_NRED_FUSION") && !force_simt() && !env_flag("CTN_SIMT_BWD");
+}
+static bool nred_fused_for(const GemmArgs& a) {
+  return nred_fusion_enabled() && a.W_hi != nullptr && a.Kd % 64 == 0 && a.O % 128 == 0 && a.F >= 16;
+}
 static int launch_gemm_nred(const GemmArgs& a, int M, cudaStream_t s) {
   // measured on B200 (M=3 x 4 s): the fused epilogue exposes the z2 loads of a GEMM whose epilogue is not overlapped
   // with anything yet, 7.70 ms/step vs 7.52 ms un-fused -> opt-in until the GEMM is persistent (CTN_NRED_FUSION=1)
-  const bool fused = env_flag("CTN_NRED_FUSION") && !force_simt() && !env_flag("CTN_SIMT_BWD") && a.W_hi != nullptr &&
-                     a.Kd % 64 == 0 && a.O % 128 == 0 && a.F >= 16;
+  const bool fused = nred_fused_for(a);
   if (fused) return launch_gemm(a, s);
   GemmArgs b = a;
   b.nred_z = nullptr;
   CTN_TRY(launch_gemm(b, s));
   return run_norm_bwd_reduce(a.D, a.nred_z, a.nred_alpha, a.st, a.nred_gamma, M, a.K, a.O, a.nred_dgamma, a.nred_dbeta,
-                             a.nred_red, a.nred_part, s);
+                             a.nred_red, a.nred_part, 1, s);
 }
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   static const bool simt_bwd = env_flag("CTN_SIMT_BWD") || env_flag("CTN_SIMT_WGRAD");
@@ -197,6 +205,7 @@ struct Plan {
   // byte offsets
   int64_t w, rowstat0, x, z1, z2, gacc, rs1, rs2, score, Wbg, c1b, c2b, W2g, c1, c2;
   int64_t g, dn2, dn1, d_score, d_w, dn0, red, part;
+  int64_t part_dw, part_nr;  // floats per block of the dwconv / norm-2 partial rows (each block keeps its own)
   int64_t pl_W1, pl_W2g, pl_Wbg, pl_Wm, pl_W1T, pl_W2T, pl_WbT, pl_WmT;  // bf16 hi planes; lo plane follows at +pl_lo
   int64_t pl_lo;
   int64_t x_stride, z_stride, rs_stride;  // bytes between consecutive blocks' buffers (0 when not stashed)
@@ -258,16 +267,16 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
     p.d_w = take(F * c.N * 4);
     p.dn0 = take(F * c.N * 4);
     p.red = take((int64_t)(p.nblk * 2 + 1) * M * 2 * 8);
-    {
+    {  // per-block partial rows (folded once per backward stage) + one shared region for the front cLN
       int64_t pf = 0;
       for (int x = 0; x < c.X; ++x) {
         const int64_t q = dwconv_bwd_partial_floats(M, p.K, c.H, c.P, 1 << x);
         pf = pf > q ? pf : q;
       }
-      const int64_t a = norm_bwd_partial_floats(M, p.K, c.H), b = norm_bwd_partial_floats(M, p.K, c.N);
-      pf = pf > a ? pf : a;
-      pf = pf > b ? pf : b;
-      p.part = take(pf * 4);
+      p.part_dw = (pf + 63) & ~(int64_t)63;
+      p.part_nr = (norm_bwd_partial_floats(M, p.K, c.H) + 63) & ~(int64_t)63;
+      const int64_t front = norm_bwd_partial_floats(M, p.K, c.N);
+      p.part = take(((int64_t)p.nblk * (p.part_dw + p.part_nr) + front) * 4);
     }
   }
   p.total = o;
@@ -470,7 +479,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       // + norm2 backward reduction over dn2 (dgamma2, dbeta2, per-sample sums) in the same kernel
       a.st = st2; a.nred_z = X.z2(b); a.nred_alpha = X.blk(b, L.a2); a.nred_gamma = X.blk(b, L.g2);
       a.nred_dgamma = gblk(b, L.g2); a.nred_dbeta = gblk(b, L.b2); a.nred_red = gln ? X.red(b, 1) : nullptr;
-      a.nred_part = X.at<float>(p.part);
+      a.nred_part = X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr) + p.part_dw;
       CTN_TRY(launch_gemm_nred(a, M, s));
     }
     {  // dW2 = g^T norm2(prelu(z2))
@@ -483,7 +492,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
                                gblk(b, L.a2), s));
     CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K, c.H,
                            c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1),
-                           gln ? X.red(b, 0) : nullptr, X.at<float>(p.part), s));
+                           gln ? X.red(b, 0) : nullptr, X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), 1, s));
     CTN_TRY(run_norm_bwd_apply(dn1, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.red(b, 0), M, K, c.H,
                                gblk(b, L.a1), s));
     {  // dW1 = dz1^T x
@@ -498,6 +507,23 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       a.W_lo = X.at<char>(p.pl_W1T + p.pl_lo) + (int64_t)b * c.H * c.B * 2;
       a.res = g_cur;
       CTN_TRY(launch_gemm(a, s));
+    }
+    if (b % c.X == 0) {  // first block of the repeat = last of its stage: fold the stage's partial rows in one launch
+      FoldBatch fb;
+      int n = 0;
+      for (int bb = b; bb < b + c.X; ++bb) {
+        const float* pb = X.at<float>(p.part) + (int64_t)bb * (p.part_dw + p.part_nr);
+        if (n + 2 > FOLD_MAX) {
+          CTN_TRY(run_fold_batch(fb, n, s));
+          n = 0;
+        }
+        fb.e[n++] = FoldEntry{pb, dwconv_bwd_blocks(M, K, 1 << (bb % c.X)), c.H, c.P, gblk(bb, L.Wd), gblk(bb, L.g1),
+                              gblk(bb, L.b1)};
+        const bool nr_fused = nred_fusion_enabled() && c.B % 64 == 0 && c.H % 128 == 0 && F >= 16;  // see launch_gemm_nred
+        if (!nr_fused)
+          fb.e[n++] = FoldEntry{pb + p.part_dw, norm_bwd_blocks(M, K), c.H, 0, nullptr, gblk(bb, L.g2), gblk(bb, L.b2)};
+      }
+      CTN_TRY(run_fold_batch(fb, n, s));
     }
   }
   if (!(stage_lo <= c.R + 1 && c.R + 1 < stage_hi)) return 0;
@@ -516,7 +542,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
     CTN_TRY(launch_gemm(a, s));
   }
   CTN_TRY(run_norm_bwd_reduce(dn0, w, nullptr, st0, X.params + L.g0, M, K, c.N, grads + L.g0, grads + L.b0, nullptr,
-                              X.at<float>(p.part), s));
+                              X.at<float>(p.part) + (int64_t)nblk * (p.part_dw + p.part_nr), 0, s));
   CTN_TRY(run_norm_bwd_apply(dn0, w, nullptr, st0, X.params + L.g0, nullptr, M, K, c.N, nullptr, s));
   return run_encoder_bwd(mixture, w, dn0, d_w, M, p.T, c.N, c.L, grads + L.U, s);
 }
