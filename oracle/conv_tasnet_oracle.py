@@ -292,3 +292,25 @@ def train_step_grads(cfg: Config, sd, mixture, source, lengths):
     names = list(params)
     grads = torch.autograd.grad(loss, [params[k] for k in names])
     return loss.detach(), est_masked.detach(), dict(zip(names, grads)), max_snr.detach(), reordered.detach()
+
+
+# --------------------------------------------------------------------------------------
+# evaluation metric (src/evaluate.py:94-130), numpy like the reference
+# --------------------------------------------------------------------------------------
+def cal_SISNR_np(ref_sig, out_sig, eps=1e-8):
+    """src/evaluate.py:114-130"""
+    import numpy as np
+    ref_sig = ref_sig - np.mean(ref_sig)
+    out_sig = out_sig - np.mean(out_sig)
+    ref_energy = np.sum(ref_sig ** 2) + eps
+    proj = np.sum(ref_sig * out_sig) * ref_sig / ref_energy
+    noise = out_sig - proj
+    ratio = np.sum(proj ** 2) / (np.sum(noise ** 2) + eps)
+    return 10 * np.log(ratio + eps) / np.log(10.0)
+
+
+def cal_SISNRi_np(src_ref, src_est, mix):
+    """src/evaluate.py:94-111 (two sources)"""
+    s1, s2 = cal_SISNR_np(src_ref[0], src_est[0]), cal_SISNR_np(src_ref[1], src_est[1])
+    b1, b2 = cal_SISNR_np(src_ref[0], mix), cal_SISNR_np(src_ref[1], mix)
+    return ((s1 - b1) + (s2 - b2)) / 2

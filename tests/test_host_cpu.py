@@ -123,3 +123,26 @@ def test_remove_pad_matches_reference_semantics():
     assert out[0].shape == (3, 5) and out[1].shape == (3, 2) and np.array_equal(out[1], x[1, :, :2].numpy())
     out = remove_pad(x[:, 0], torch.tensor([4, 1]))
     assert out[0].shape == (4,) and out[1].shape == (1,)
+
+
+def test_batched_sisnri_matches_reference_metric():
+    """conv_tasnet_b200.evaluate (batched, masked, device-side) against the numpy restatement of src/evaluate.py:94-130
+    applied per utterance after remove_pad, like the reference's evaluation loop."""
+    from conv_tasnet_b200.evaluate import cal_SISNR, cal_SISNRi, cal_SISNRi_batch
+    from conv_tasnet_b200.utils import remove_pad
+    g = torch.Generator().manual_seed(5)
+    B, C, T = 4, 2, 900
+    src = torch.randn(B, C, T, generator=g) * 0.05
+    lens = torch.tensor([900, 640, 900, 123])
+    for b, n in enumerate(lens.tolist()):
+        src[b, :, n:] = 0
+    mix = src.sum(1)
+    est = src + 0.02 * torch.randn(B, C, T, generator=g)
+    got = cal_SISNRi_batch(src, est, mix, lens)
+    for b, (s, e, m) in enumerate(zip(remove_pad(src, lens), remove_pad(est, lens), remove_pad(mix, lens))):
+        want = O.cal_SISNRi_np(s.astype(np.float64), e.astype(np.float64), m.astype(np.float64))
+        assert abs(got[b].item() - want) < 1e-6
+    want = O.cal_SISNR_np(src[0, 0].double().numpy(), est[0, 0].double().numpy())
+    assert abs(cal_SISNR(src[0, 0], est[0, 0]).item() - want) < 1e-9
+    assert abs(cal_SISNRi(src[0], est[0], mix[0]).item()
+               - O.cal_SISNRi_np(src[0].double().numpy(), est[0].double().numpy(), mix[0].double().numpy())) < 1e-9
