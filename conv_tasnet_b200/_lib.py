@@ -29,6 +29,8 @@ SIGNATURES = {
     "ctn_workspace_bytes": (c_i64, [_P, c_i32, c_i32, c_i32]),
     "ctn_grad_bucket": (c_i32, [_P, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "ctn_model_forward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "ctn_norm_state_floats": (c_i64, [_P]),
+    "ctn_model_forward_bn": (c_i32, [_P, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "ctn_model_backward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "ctn_model_backward_stage": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "ctn_pit_workspace_bytes": (c_i64, [c_i32, c_i32]),
@@ -96,10 +98,6 @@ def stream():
 
 
 def make_config(N, L, B, H, P, X, R, C, norm_type, causal, mask_nonlinear):
-    norm = {"gLN": 0, "cLN": 1}.get(norm_type)
-    if norm is None:
-        raise NotImplementedError(
-            f"norm_type={norm_type!r}: only 'gLN' and 'cLN' are on the B200 hot path (the reference's BatchNorm "
-            "fall-through, src/conv_tasnet.py:306-309, is out of scope)")
+    norm = {"gLN": 0, "cLN": 1}.get(norm_type, 2)  # anything else is BatchNorm, like chose_norm (src/conv_tasnet.py:306)
     mask = {"relu": 0, "softmax": 1}.get(mask_nonlinear, -1)
     return CtnConfig(N, L, B, H, P, X, R, C, norm, 1 if causal else 0, mask)

@@ -66,27 +66,36 @@ class Decoder(nn.Module):
         self.basis_signals = _Weight(L, N)  # nn.Linear(N, L, bias=False), src/conv_tasnet.py:129
 
 
-def _ds_conv(B, H, P, causal):
+def _chose_norm(norm_type, channel_size):
+    """Parameter holder at the position of chose_norm (src/conv_tasnet.py:298-309): gamma/beta [1,C,1] for gLN / cLN,
+    and for anything else the reference's nn.BatchNorm1d itself (weight, bias, running_mean, running_var,
+    num_batches_tracked: same state_dict keys, same defaults; its forward is never called)."""
+    if norm_type in ("gLN", "cLN"):
+        return _Norm(channel_size)
+    return nn.BatchNorm1d(channel_size)
+
+
+def _ds_conv(B, H, P, causal, norm_type):
     mods = [_Weight(H, 1, P)]  # depthwise, src/conv_tasnet.py:253
     if causal:
         mods.append(_Slot())  # Chomp1d
-    mods += [_PReLU(), _Norm(H), _Weight(B, H, 1)]
+    mods += [_PReLU(), _chose_norm(norm_type, H), _Weight(B, H, 1)]
     net = _Seq(*mods)
     holder = nn.Module()
     holder.net = net
     return holder
 
 
-def _temporal_block(B, H, P, causal):
+def _temporal_block(B, H, P, causal, norm_type):
     holder = nn.Module()
-    holder.net = _Seq(_Weight(H, B, 1), _PReLU(), _Norm(H), _ds_conv(B, H, P, causal))
+    holder.net = _Seq(_Weight(H, B, 1), _PReLU(), _chose_norm(norm_type, H), _ds_conv(B, H, P, causal, norm_type))
     return holder
 
 
 class TemporalConvNet(nn.Module):
-    def __init__(self, N, B, H, P, X, R, C, causal):
+    def __init__(self, N, B, H, P, X, R, C, causal, norm_type="gLN"):
         super().__init__()
-        repeats = [_Seq(*[_temporal_block(B, H, P, causal) for _ in range(X)]) for _ in range(R)]
+        repeats = [_Seq(*[_temporal_block(B, H, P, causal, norm_type) for _ in range(X)]) for _ in range(R)]
         self.network = _Seq(_Norm(N), _Weight(B, N, 1), _Seq(*repeats), _Weight(C * N, B, 1))
 
 
@@ -123,7 +132,7 @@ class ConvTasNet(nn.Module):
             # let _run_forward raise the ValueError
             self._cfg.mask_nonlinear = 0
         self.encoder = Encoder(L, N)
-        self.separator = TemporalConvNet(N, B, H, P, X, R, C, causal)
+        self.separator = TemporalConvNet(N, B, H, P, X, R, C, causal, norm_type)
         self.decoder = Decoder(N, L)
         for p in self.parameters():  # includes gamma/beta [1,C,1] (src/conv_tasnet.py:41-43)
             if p.dim() > 1:
@@ -136,6 +145,10 @@ class ConvTasNet(nn.Module):
         self._grad_sync = None  # set by data_parallel.ShardedDataParallel
         self._overwrite_next = False  # set by optim.FusedAdam: the next backward overwrites the flat gradients
         self._plist = None
+        # BatchNorm branch: running statistics of every nn.BatchNorm1d in ONE flat buffer (the C ABI's norm_state)
+        self._bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm1d)]
+        self._bn_state = None
+        self._bn_count = None
 
     # ------------------------------------------------------------------ flat parameter storage
     def _param_layout(self):
@@ -156,6 +169,12 @@ class ConvTasNet(nn.Module):
         for i in (0, len(self._plist) // 2, len(self._plist) - 1):
             if self._plist[i].data_ptr() != base + 4 * offs[i]:
                 return False
+        if self._bns:
+            H, st = self.H, self._bn_state
+            if st is None or self._bns[0].running_mean.data_ptr() != st.data_ptr() \
+                    or self._bns[-1].running_var.data_ptr() != st.data_ptr() + 4 * (2 * len(self._bns) - 1) * H \
+                    or self._bns[-1].num_batches_tracked.data_ptr() != self._bn_count.data_ptr() + 8 * (len(self._bns) - 1):
+                return False
         return True
 
     def _flatten(self):
@@ -175,6 +194,18 @@ class ConvTasNet(nn.Module):
         self._flat, self._plist = flat, plist
         self._flat_grad = None
         self._ws_cache = {}
+        if self._bns:  # modules() order = block order, norm 1 then norm 2: the layout ctn_model_forward_bn expects
+            H = self.H
+            state = torch.empty(2 * len(self._bns) * H, dtype=torch.float32, device=dev)
+            count = torch.empty(len(self._bns), dtype=torch.int64, device=dev)
+            for i, m in enumerate(self._bns):
+                state[2 * i * H:(2 * i + 1) * H].copy_(m.running_mean)
+                state[(2 * i + 1) * H:(2 * i + 2) * H].copy_(m.running_var)
+                count[i] = m.num_batches_tracked
+                m.running_mean = state[2 * i * H:(2 * i + 1) * H]
+                m.running_var = state[(2 * i + 1) * H:(2 * i + 2) * H]
+                m.num_batches_tracked = count[i]
+            self._bn_state, self._bn_count = state, count
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -237,9 +268,17 @@ class ConvTasNet(nn.Module):
         with torch.cuda.device(mixture.device):
             ws, cached = self._workspace(M, T, training)
             est = torch.empty(M, self.C, T, dtype=torch.float32, device=mixture.device)
-            _lib.check(_lib.lib().ctn_model_forward(ctypes.byref(self._cfg), _lib.ptr(flat), _lib.ptr(mixture), M, T,
-                                                    _lib.ptr(est), _lib.ptr(ws), ws.numel(), 1 if training else 0,
-                                                    _lib.stream()))
+            if self._bns:  # nn.BatchNorm1d semantics: batch statistics + running update in .train(), running in .eval()
+                _lib.check(_lib.lib().ctn_model_forward_bn(
+                    ctypes.byref(self._cfg), _lib.ptr(flat), _lib.ptr(self._bn_state), _lib.ptr(mixture), M, T,
+                    _lib.ptr(est), _lib.ptr(ws), ws.numel(), 1 if training else 0, 1 if self.training else 0,
+                    _lib.stream()))
+                if self.training:
+                    self._bn_count += 1
+            else:
+                _lib.check(_lib.lib().ctn_model_forward(ctypes.byref(self._cfg), _lib.ptr(flat), _lib.ptr(mixture), M,
+                                                        T, _lib.ptr(est), _lib.ptr(ws), ws.numel(),
+                                                        1 if training else 0, _lib.stream()))
         token = None
         if training:
             token = _Token()

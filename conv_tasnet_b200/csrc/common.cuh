@@ -70,6 +70,8 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // ---- normalisation statistics -----------------------------------------------------------
 // gLN: per-sample (sum, sumsq) accumulated in fp64 by the producing kernel; consumers derive
 //      mean / rstd on the fly (no finalize kernel).  cLN: per-frame (mean, rstd) floats.
+// Both pointers null = identity (mu 0, r 1): the BatchNorm branch, whose per-channel scale/shift travel as the
+// consumers' gamma / beta vectors (batchnorm.cu).
 struct NormStats {
   const double* acc;  // [M][2] or nullptr
   const float* row;   // [F][2] or nullptr
@@ -81,6 +83,9 @@ __device__ __forceinline__ void load_stats(const NormStats& s, int m, int64_t f,
     float2 v = reinterpret_cast<const float2*>(s.row)[f];
     mu = v.x;
     r = v.y;
+  } else if (s.acc == nullptr) {
+    mu = 0.f;
+    r = 1.f;
   } else {
     double S = s.acc[2 * m], S2 = s.acc[2 * m + 1];
     double mean = S * s.inv_count;

@@ -17,7 +17,7 @@ struct StatCache {
 
 __device__ __forceinline__ void stat_cache_init(StatCache& c, const NormStats& s, int m_lo, int m_hi) {
   if (threadIdx.x == 0) c.m_lo = m_lo;
-  if (s.row == nullptr && s.acc != nullptr && (int)threadIdx.x <= m_hi - m_lo && threadIdx.x < 16) {
+  if (s.row == nullptr && (int)threadIdx.x <= m_hi - m_lo && threadIdx.x < 16) {
     float mu, r;
     load_stats(s, m_lo + threadIdx.x, 0, mu, r);
     c.v[threadIdx.x] = make_float2(mu, r);

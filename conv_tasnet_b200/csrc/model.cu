@@ -63,6 +63,13 @@ int run_decoder_fwd(const float*, const float*, const float*, int, int, int, int
 int run_decoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, float*,
                     float*, float*, cudaStream_t);
 
+int run_bn_forward_stats(const float*, const float*, const float*, const float*, float*, float*, int64_t, int, int, double*,
+                         float*, float*, float*, float*, float*, cudaStream_t);
+int run_bn_bwd_finalize(const float*, const float*, const float*, const float*, const float*, int64_t, int, float*, float*,
+                        float*, float*, cudaStream_t);
+int run_bn_bwd_apply(float*, const float*, const float*, const float*, const float*, const float*, const float*, int64_t,
+                     int, float*, cudaStream_t);
+
 bool tc_gemm_eligible(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 bool tc_wgrad_eligible(const WgradArgs& a);
@@ -129,16 +136,17 @@ static bool nred_fusion_enabled() {
 static bool nred_fused_for(const GemmArgs& a) {
   return nred_fusion_enabled() && a.W_hi != nullptr && a.Kd % 64 == 0 && a.O % 128 == 0 && a.F >= 16;
 }
-static int launch_gemm_nred(const GemmArgs& a, int M, cudaStream_t s) {
+static int launch_gemm_nred(const GemmArgs& a, int M, int defer_fold, cudaStream_t s) {
   // measured on B200 (M=3 x 4 s): the fused epilogue exposes the z2 loads of a GEMM whose epilogue is not overlapped
-  // with anything yet, 7.70 ms/step vs 7.52 ms un-fused -> opt-in until the GEMM is persistent (CTN_NRED_FUSION=1)
-  const bool fused = nred_fused_for(a);
+  // with anything yet, 7.70 ms/step vs 7.52 ms un-fused -> opt-in until the GEMM is persistent (CTN_NRED_FUSION=1).
+  // defer_fold = 0 (BatchNorm: the per-channel sums are needed right away) always takes the un-fused route.
+  const bool fused = defer_fold && nred_fused_for(a);
   if (fused) return launch_gemm(a, s);
   GemmArgs b = a;
   b.nred_z = nullptr;
   CTN_TRY(launch_gemm(b, s));
   return run_norm_bwd_reduce(a.D, a.nred_z, a.nred_alpha, a.st, a.nred_gamma, M, a.K, a.O, a.nred_dgamma, a.nred_dbeta,
-                             a.nred_red, a.nred_part, 1, s);
+                             a.nred_red, a.nred_part, defer_fold, s);
 }
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   static const bool simt_bwd = env_flag("CTN_SIMT_BWD") || env_flag("CTN_SIMT_WGRAD");
@@ -190,8 +198,8 @@ static int validate(const ctn_config* c) {
   CTN_REQUIRE(c->P <= 8, "config: P <= 8 supported (got %d)", c->P);
   CTN_REQUIRE(c->X <= 20, "config: X <= 20 (dilation 2^x)");
   CTN_REQUIRE(c->L <= 32 && c->N <= 512, "config: L <= 32 and N <= 512 supported (got L=%d N=%d)", c->L, c->N);
-  CTN_REQUIRE(c->norm_type == CTN_NORM_GLN || c->norm_type == CTN_NORM_CLN,
-              "config: norm_type must be gLN or cLN (the BatchNorm branch is outside the hot path)");
+  CTN_REQUIRE(c->norm_type == CTN_NORM_GLN || c->norm_type == CTN_NORM_CLN || c->norm_type == CTN_NORM_BN,
+              "config: norm_type must be 0 (gLN), 1 (cLN) or 2 (BN)");
   CTN_REQUIRE(c->causal || (c->P % 2 == 1), "config: non-causal needs odd P");
   CTN_REQUIRE(c->mask_nonlinear == CTN_MASK_RELU || c->mask_nonlinear == CTN_MASK_SOFTMAX,
               "Unsupported mask non-linear function");
@@ -205,6 +213,7 @@ struct Plan {
   // byte offsets
   int64_t w, rowstat0, x, z1, z2, gacc, rs1, rs2, score, Wbg, c1b, c2b, W2g, c1, c2;
   int64_t g, dn2, dn1, d_score, d_w, dn0, red, part;
+  int64_t bn_acc, bn_fwd, bn_ab, bn_coef, bn_mode;  // BatchNorm slots, structure-of-arrays over (block, norm)
   int64_t part_dw, part_nr;  // floats per block of the dwconv / norm-2 partial rows (each block keeps its own)
   int64_t pl_W1, pl_W2g, pl_Wbg, pl_Wm, pl_W1T, pl_W2T, pl_WbT, pl_WmT;  // bf16 hi planes; lo plane follows at +pl_lo
   int64_t pl_lo;
@@ -237,6 +246,14 @@ static Plan make_plan(const ctn_config& c, int M, int T, int training) {
   p.rs_stride = cln ? al256(F * 2 * 4) : 0;
   p.rs1 = o; o += p.rs_stride * (training ? p.nblk : 1);
   p.rs2 = o; o += p.rs_stride * (training ? p.nblk : 1);
+  if (c.norm_type == CTN_NORM_BN) {  // per (block, norm): fp64 (sum, sumsq)[H]; (mean, rstd, s, t)[H]; (A, B)[H]; (ca, cq)[H]; mode
+    const int64_t ns = (int64_t)p.nblk * 2;
+    p.bn_acc = take(ns * 2 * c.H * 8);
+    p.bn_fwd = take(ns * 4 * c.H * 4);
+    p.bn_ab = take(ns * 2 * c.H * 4);
+    p.bn_coef = take(ns * 2 * c.H * 4);
+    p.bn_mode = take(ns * 4);
+  }
   p.score = take(F * c.C * c.N * 4);
   p.Wbg = take((int64_t)c.B * c.N * 4);
   p.c1b = take(c.B * 4);
@@ -290,6 +307,8 @@ struct Ctx {
   const float* params;
   char* ws;
   cudaStream_t s;
+  float* bn_state = nullptr;  // BN running statistics [nblk][rm1 H | rv1 H | rm2 H | rv2 H] (forward only)
+  int bn_batch = 1;           // BN: 1 = batch statistics (+ running update), 0 = running statistics
   template <typename T>
   T* at(int64_t off) const { return reinterpret_cast<T*>(ws + off); }
   const float* blk(int b, int64_t off) const { return params + L.blk0 + (int64_t)b * L.blk_stride + off; }
@@ -297,9 +316,27 @@ struct Ctx {
   float* x(int b) const { return at<float>(p.x + p.x_stride * (p.training ? b : (b & 1))); }
   float* z1(int b) const { return at<float>(p.z1 + p.z_stride * (p.training ? b : 0)); }
   float* z2(int b) const { return at<float>(p.z2 + p.z_stride * (p.training ? b : 0)); }
+  // BatchNorm slot views
+  int64_t bn_slot(int b, int which) const { return (int64_t)b * 2 + which; }
+  double* bn_acc(int b, int which) const { return at<double>(p.bn_acc) + bn_slot(b, which) * 2 * c.H; }
+  float* bn_fwd(int b, int which, int field) const {  // field: 0 mean, 1 rstd, 2 s, 3 t
+    return at<float>(p.bn_fwd) + (bn_slot(b, which) * 4 + field) * c.H;
+  }
+  float* bn_ab(int b, int which, int field) const { return at<float>(p.bn_ab) + (bn_slot(b, which) * 2 + field) * c.H; }
+  float* bn_coef(int b, int which, int field) const { return at<float>(p.bn_coef) + (bn_slot(b, which) * 2 + field) * c.H; }
+  float* bn_mode(int b, int which) const { return at<float>(p.bn_mode) + bn_slot(b, which); }
+  // (gamma, beta) as the consumers see them: the parameters, or BatchNorm's per-channel (s, t)
+  const float* gam(int b, int which) const {
+    return c.norm_type == CTN_NORM_BN ? bn_fwd(b, which, 2) : blk(b, which ? L.g2 : L.g1);
+  }
+  const float* bet(int b, int which) const {
+    return c.norm_type == CTN_NORM_BN ? bn_fwd(b, which, 3) : blk(b, which ? L.b2 : L.b1);
+  }
   NormStats stats(int b, int which) const {
     NormStats st;
-    if (c.norm_type == CTN_NORM_GLN) {
+    if (c.norm_type == CTN_NORM_BN) {
+      st.acc = nullptr; st.row = nullptr; st.inv_count = 0.0;  // identity: the normalisation lives in (s, t)
+    } else if (c.norm_type == CTN_NORM_GLN) {
       st.acc = at<double>(p.gacc) + ((int64_t)b * 2 + which) * p.M * 2;
       st.row = nullptr;
       st.inv_count = 1.0 / ((double)p.K * (double)c.H);
@@ -327,6 +364,19 @@ static int check_io(const ctn_config* cfg, int M, int T, const void* ws, int64_t
   return 0;
 }
 
+// BatchNorm of block b, norm `which` (0: after the first PReLU, 1: after the depthwise conv's PReLU): batch statistics of
+// prelu(z) (training) or the running statistics (evaluation) -> per-channel (mean, rstd, s, t) in the block's slot
+static int bn_forward(const Ctx& X, int b, int which, const float* z) {
+  const ctn_config& c = X.c;
+  const ParamLayout& L = X.L;
+  CTN_REQUIRE(X.bn_state != nullptr, "norm_type BN needs the running-statistics buffer: call ctn_model_forward_bn");
+  float* rm = X.bn_state + ((int64_t)b * 4 + which * 2) * c.H;
+  return run_bn_forward_stats(z, X.blk(b, which ? L.a2 : L.a1), X.blk(b, which ? L.g2 : L.g1),
+                              X.blk(b, which ? L.b2 : L.b1), rm, rm + c.H, X.p.F, c.H, X.bn_batch, X.bn_acc(b, which),
+                              X.bn_fwd(b, which, 0), X.bn_fwd(b, which, 1), X.bn_fwd(b, which, 2),
+                              X.bn_fwd(b, which, 3), X.bn_mode(b, which), X.s);
+}
+
 static int model_forward(const Ctx& X, const float* mixture, float* est) {
   const ctn_config& c = X.c;
   const Plan& p = X.p;
@@ -334,14 +384,17 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
   const int M = p.M, K = p.K, nblk = p.nblk;
   const int64_t F = p.F;
   cudaStream_t s = X.s;
-  const bool gln = c.norm_type == CTN_NORM_GLN;
+  const bool gln = c.norm_type == CTN_NORM_GLN, cln = c.norm_type == CTN_NORM_CLN, bn = c.norm_type == CTN_NORM_BN;
 
   if (gln) CTN_CUDA(cudaMemsetAsync(X.at<char>(p.gacc), 0, (size_t)nblk * 2 * M * 2 * 8, s));
-  // norm-fold constants for the bottleneck and every block's pointwise conv (one launch each)
+  if (bn) CTN_CUDA(cudaMemsetAsync(X.at<char>(p.bn_acc), 0, (size_t)nblk * 2 * 2 * c.H * 8, s));
+  // norm-fold constants for the bottleneck and every block's pointwise conv (one launch each).  BatchNorm: the
+  // per-channel scale of a block is only known once its statistics are, so its fold happens inside the block loop.
   CTN_TRY(run_prep_normfold(X.params + L.Wb, X.params + L.g0, X.params + L.b0, c.B, c.N, 1, 0, X.at<float>(p.Wbg),
                             X.at<float>(p.c1b), X.at<float>(p.c2b), 0, 0, s));
-  CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
-                            X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
+  if (!bn)
+    CTN_TRY(run_prep_normfold(X.blk(0, L.W2), X.blk(0, L.g2), X.blk(0, L.b2), c.B, c.H, nblk, L.blk_stride,
+                              X.at<float>(p.W2g), X.at<float>(p.c1), X.at<float>(p.c2), (int64_t)c.B * c.H, c.B, s));
   // split planes of every forward GEMM weight (batched over the blocks).  Training: TF32 split (fp32-class forward,
   // needed for gradient parity).  Inference: bf16 split — 1e-5-class outputs (budget 1e-4), half the
   // tensor-core and shared-memory cost.
@@ -350,8 +403,9 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
   if (fwd_tf32) {
     CTN_TRY(run_split_planes_tf32(X.blk(0, L.W1), (int64_t)c.H * c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
                                   X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, s));
-    CTN_TRY(run_split_planes_tf32(X.at<float>(p.W2g), (int64_t)c.B * c.H, nblk, (int64_t)c.B * c.H,
-                                  X.at<char>(p.pl_W2g), X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, s));
+    if (!bn)
+      CTN_TRY(run_split_planes_tf32(X.at<float>(p.W2g), (int64_t)c.B * c.H, nblk, (int64_t)c.B * c.H,
+                                    X.at<char>(p.pl_W2g), X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, s));
     CTN_TRY(run_split_planes_tf32(X.at<float>(p.Wbg), (int64_t)c.B * c.N, 1, 0, X.at<char>(p.pl_Wbg),
                                   X.at<char>(p.pl_Wbg + p.pl_lo), 0, s));
     CTN_TRY(run_split_planes_tf32(X.params + L.Wm, (int64_t)c.C * c.N * c.B, 1, 0, X.at<char>(p.pl_Wm),
@@ -359,8 +413,9 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
   } else {
     CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1),
                              X.at<char>(p.pl_W1 + p.pl_lo), (int64_t)c.H * c.B, 0, s));
-    CTN_TRY(run_split_planes(X.at<float>(p.W2g), c.B, c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
-                             X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, 0, s));
+    if (!bn)
+      CTN_TRY(run_split_planes(X.at<float>(p.W2g), c.B, c.H, nblk, (int64_t)c.B * c.H, X.at<char>(p.pl_W2g),
+                               X.at<char>(p.pl_W2g + p.pl_lo), (int64_t)c.B * c.H, 0, s));
     CTN_TRY(run_split_planes(X.at<float>(p.Wbg), c.B, c.N, 1, 0, X.at<char>(p.pl_Wbg), X.at<char>(p.pl_Wbg + p.pl_lo),
                              0, 0, s));
     CTN_TRY(run_split_planes(X.params + L.Wm, c.C * c.N, c.B, 1, 0, X.at<char>(p.pl_Wm), X.at<char>(p.pl_Wm + p.pl_lo),
@@ -389,10 +444,22 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.tf32 = fwd_tf32;
       CTN_TRY(launch_gemm(a, s));
     }
-    if (!gln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
-    CTN_TRY(run_dwconv_fwd(X.z1(b), X.blk(b, L.a1), X.stats(b, 0), X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K,
+    if (cln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
+    if (bn) CTN_TRY(bn_forward(X, b, 0, X.z1(b)));
+    CTN_TRY(run_dwconv_fwd(X.z1(b), X.blk(b, L.a1), X.stats(b, 0), X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K,
                            c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s));
-    if (!gln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s));
+    if (cln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s));
+    if (bn) {  // statistics of prelu(z2) -> (s, t) -> this block's folded pointwise weight and its operand planes
+      CTN_TRY(bn_forward(X, b, 1, X.z2(b)));
+      float* W2g = X.at<float>(p.W2g) + (int64_t)b * c.B * c.H;
+      CTN_TRY(run_prep_normfold(X.blk(b, L.W2), X.gam(b, 1), X.bet(b, 1), c.B, c.H, 1, 0, W2g,
+                                X.at<float>(p.c1) + (int64_t)b * c.B, X.at<float>(p.c2) + (int64_t)b * c.B, 0, 0, s));
+      char* hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * esz;
+      if (fwd_tf32)
+        CTN_TRY(run_split_planes_tf32(W2g, (int64_t)c.B * c.H, 1, 0, hi, hi + p.pl_lo, 0, s));
+      else
+        CTN_TRY(run_split_planes(W2g, c.B, c.H, 1, 0, hi, hi + p.pl_lo, 0, 0, s));
+    }
     {  // out = x + norm2(prelu(z2)) W2^T with norm2 folded
       GemmArgs a = {};
       a.A = X.z2(b); a.W = X.at<float>(p.W2g) + (int64_t)b * c.B * c.H; a.D = X.x(b + 1);
@@ -427,8 +494,22 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
   const int M = p.M, K = p.K, nblk = p.nblk;
   const int64_t F = p.F;
   cudaStream_t s = X.s;
-  const bool gln = c.norm_type == CTN_NORM_GLN;
+  const bool gln = c.norm_type == CTN_NORM_GLN, bn = c.norm_type == CTN_NORM_BN;
   auto gblk = [&](int b, int64_t off) { return grads + L.blk0 + (int64_t)b * L.blk_stride + off; };
+  // backward through one norm + the PReLU in front of it, in place over dn (gradient w.r.t. the normalised activation)
+  auto norm_apply = [&](int b, int which, float* dn, const float* z) -> int {
+    const float* alpha = X.blk(b, which ? L.a2 : L.a1);
+    float* dalpha = gblk(b, which ? L.a2 : L.a1);
+    if (!bn)
+      return run_norm_bwd_apply(dn, z, alpha, X.stats(b, which), X.blk(b, which ? L.g2 : L.g1), X.red(b, which), M, K, c.H,
+                                dalpha, s);
+    // BatchNorm: the folded per-channel sums -> dweight, dbias and the coefficients of the apply pass
+    CTN_TRY(run_bn_bwd_finalize(X.bn_ab(b, which, 0), X.bn_ab(b, which, 1), X.bn_fwd(b, which, 0), X.bn_fwd(b, which, 1),
+                                X.bn_mode(b, which), F, c.H, gblk(b, which ? L.g2 : L.g1), gblk(b, which ? L.b2 : L.b1),
+                                X.bn_coef(b, which, 0), X.bn_coef(b, which, 1), s));
+    return run_bn_bwd_apply(dn, z, alpha, X.bn_fwd(b, which, 2), X.bn_fwd(b, which, 0), X.bn_coef(b, which, 0),
+                            X.bn_coef(b, which, 1), F, c.H, dalpha, s);
+  };
 
   float* w = X.at<float>(p.w);
   float* g_buf[2] = {X.at<float>(p.g), X.at<float>(p.g + al256(F * c.B * 4))};
@@ -442,6 +523,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
   float* g_cur = g_buf[0];
   if (!accumulate) CTN_CUDA(cudaMemsetAsync(grads, 0, (size_t)L.total * 4, s));
   CTN_CUDA(cudaMemsetAsync(X.at<char>(p.red), 0, (size_t)(nblk * 2 + 1) * M * 2 * 8, s));
+  if (bn) CTN_CUDA(cudaMemsetAsync(X.at<char>(p.bn_ab), 0, (size_t)nblk * 2 * 2 * c.H * 4, s));
   // transposed bf16 hi/lo weight planes for the data-gradient GEMMs
   CTN_TRY(run_split_planes(X.blk(0, L.W1), c.H, c.B, nblk, L.blk_stride, X.at<char>(p.pl_W1T),
                            X.at<char>(p.pl_W1T + p.pl_lo), (int64_t)c.H * c.B, 1, s));
@@ -477,24 +559,26 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       a.W_hi = X.at<char>(p.pl_W2T) + (int64_t)b * c.B * c.H * 2;
       a.W_lo = X.at<char>(p.pl_W2T + p.pl_lo) + (int64_t)b * c.B * c.H * 2;
       // + norm2 backward reduction over dn2 (dgamma2, dbeta2, per-sample sums) in the same kernel
-      a.st = st2; a.nred_z = X.z2(b); a.nred_alpha = X.blk(b, L.a2); a.nred_gamma = X.blk(b, L.g2);
-      a.nred_dgamma = gblk(b, L.g2); a.nred_dbeta = gblk(b, L.b2); a.nred_red = gln ? X.red(b, 1) : nullptr;
+      // (BatchNorm: the sums land in the block's (A, B) slot and are folded at once)
+      a.st = st2; a.nred_z = X.z2(b); a.nred_alpha = X.blk(b, L.a2); a.nred_gamma = X.gam(b, 1);
+      a.nred_dgamma = bn ? X.bn_ab(b, 1, 1) : gblk(b, L.g2);
+      a.nred_dbeta = bn ? X.bn_ab(b, 1, 0) : gblk(b, L.b2);
+      a.nred_red = gln ? X.red(b, 1) : nullptr;
       a.nred_part = X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr) + p.part_dw;
-      CTN_TRY(launch_gemm_nred(a, M, s));
+      CTN_TRY(launch_gemm_nred(a, M, bn ? 0 : 1, s));
     }
     {  // dW2 = g^T norm2(prelu(z2))
       WgradArgs wa = {};
       wa.G = g_cur; wa.Act = X.z2(b); wa.dW = gblk(b, L.W2); wa.F = F; wa.O = c.B; wa.I = c.H; wa.K = K;
-      wa.alpha = X.blk(b, L.a2); wa.gamma = X.blk(b, L.g2); wa.beta = X.blk(b, L.b2); wa.st = st2;
+      wa.alpha = X.blk(b, L.a2); wa.gamma = X.gam(b, 1); wa.beta = X.bet(b, 1); wa.st = st2;
       CTN_TRY(launch_wgrad(wa, s));
     }
-    CTN_TRY(run_norm_bwd_apply(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), M, K, c.H,
-                               gblk(b, L.a2), s));
-    CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.blk(b, L.b1), X.blk(b, L.Wd), M, K, c.H,
-                           c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1),
-                           gln ? X.red(b, 0) : nullptr, X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), 1, s));
-    CTN_TRY(run_norm_bwd_apply(dn1, X.z1(b), X.blk(b, L.a1), st1, X.blk(b, L.g1), X.red(b, 0), M, K, c.H,
-                               gblk(b, L.a1), s));
+    CTN_TRY(norm_apply(b, 1, dn2, X.z2(b)));
+    CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K, c.H,
+                           c.P, dil, c.causal, dn1, gblk(b, L.Wd), bn ? X.bn_ab(b, 0, 1) : gblk(b, L.g1),
+                           bn ? X.bn_ab(b, 0, 0) : gblk(b, L.b1), gln ? X.red(b, 0) : nullptr,
+                           X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), bn ? 0 : 1, s));
+    CTN_TRY(norm_apply(b, 0, dn1, X.z1(b)));
     {  // dW1 = dz1^T x
       WgradArgs wa = {};
       wa.G = dn1; wa.Act = X.x(b); wa.dW = gblk(b, L.W1); wa.F = F; wa.O = c.H; wa.I = c.B; wa.K = K;
@@ -508,7 +592,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       a.res = g_cur;
       CTN_TRY(launch_gemm(a, s));
     }
-    if (b % c.X == 0) {  // first block of the repeat = last of its stage: fold the stage's partial rows in one launch
+    if (b % c.X == 0 && !bn) {  // first block of the repeat = last of its stage: fold the stage's partial rows in one launch
       FoldBatch fb;
       int n = 0;
       for (int bb = b; bb < b + c.X; ++bb) {
@@ -609,7 +693,26 @@ int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const floa
                           float* est, void* workspace, int64_t workspace_bytes, int32_t training, cudaStream_t stream) {
   CTN_TRY(check_io(cfg, M, T, workspace, workspace_bytes, training));
   CTN_REQUIRE(params && mixture && est, "model_forward: null pointer");
+  CTN_REQUIRE(cfg->norm_type != CTN_NORM_BN, "model_forward: norm_type BN carries running statistics, call "
+              "ctn_model_forward_bn");
   Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, training), params, reinterpret_cast<char*>(workspace), stream};
+  return model_forward(X, mixture, est);
+}
+
+int64_t ctn_norm_state_floats(const ctn_config* cfg) {
+  if (validate(cfg)) return -1;
+  return cfg->norm_type == CTN_NORM_BN ? (int64_t)cfg->R * cfg->X * 4 * cfg->H : 0;
+}
+
+int32_t ctn_model_forward_bn(const ctn_config* cfg, const float* params, float* norm_state, const float* mixture,
+                             int32_t M, int32_t T, float* est, void* workspace, int64_t workspace_bytes,
+                             int32_t training, int32_t batch_stats, cudaStream_t stream) {
+  CTN_TRY(check_io(cfg, M, T, workspace, workspace_bytes, training));
+  CTN_REQUIRE(cfg->norm_type == CTN_NORM_BN, "model_forward_bn: the configuration is not norm_type BN");
+  CTN_REQUIRE(params && norm_state && mixture && est, "model_forward_bn: null pointer");
+  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, training), params, reinterpret_cast<char*>(workspace), stream};
+  X.bn_state = norm_state;
+  X.bn_batch = batch_stats ? 1 : 0;
   return model_forward(X, mixture, est);
 }
 

@@ -30,12 +30,12 @@ typedef struct CUstream_st* cudaStream_t;
 /* Hyper-parameters of ConvTasNet.__init__ (src/conv_tasnet.py:14-30). */
 typedef struct ctn_config {
   int32_t N, L, B, H, P, X, R, C;
-  int32_t norm_type;      /* 0 = gLN, 1 = cLN               (chose_norm, src/conv_tasnet.py:298-305) */
+  int32_t norm_type;      /* 0 = gLN, 1 = cLN, 2 = BatchNorm (chose_norm, src/conv_tasnet.py:298-309) */
   int32_t causal;         /* 0 / 1                          (src/conv_tasnet.py:182,264-269)        */
   int32_t mask_nonlinear; /* 0 = relu, 1 = softmax          (src/conv_tasnet.py:209-214)            */
 } ctn_config;
 
-enum { CTN_NORM_GLN = 0, CTN_NORM_CLN = 1, CTN_MASK_RELU = 0, CTN_MASK_SOFTMAX = 1 };
+enum { CTN_NORM_GLN = 0, CTN_NORM_CLN = 1, CTN_NORM_BN = 2, CTN_MASK_RELU = 0, CTN_MASK_SOFTMAX = 1 };
 
 int32_t ctn_version(void);
 const char* ctn_last_error(void);
@@ -62,6 +62,18 @@ int64_t ctn_workspace_bytes(const ctn_config* cfg, int32_t M, int32_t T, int32_t
 int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const float* mixture,
                           int32_t M, int32_t T, float* est, void* workspace, int64_t workspace_bytes,
                           int32_t training, cudaStream_t stream);
+/* The BatchNorm branch of chose_norm (src/conv_tasnet.py:306-309: nn.BatchNorm1d(H) after both PReLUs of every
+ * TemporalBlock; the front norm stays cLN, :172).  norm_state holds the running statistics, per block
+ * [running_mean1 H | running_var1 H | running_mean2 H | running_var2 H] (ctn_norm_state_floats floats; 0 unless BN).
+ * batch_stats != 0 is nn.Module.train(): normalise with the batch statistics over (M, K) and update norm_state
+ * (momentum 0.1, unbiased variance, eps 1e-5 — the nn.BatchNorm1d defaults); batch_stats == 0 is .eval(): normalise
+ * with norm_state.  `training` keeps its meaning (stash for ctn_model_backward, which needs nothing extra: it
+ * differentiates through the batch statistics when the forward used them).  BatchNorm weight / bias take the place
+ * of gamma / beta in the parameter layout (same offsets, [H] each). */
+int64_t ctn_norm_state_floats(const ctn_config* cfg);
+int32_t ctn_model_forward_bn(const ctn_config* cfg, const float* params, float* norm_state, const float* mixture,
+                             int32_t M, int32_t T, float* est, void* workspace, int64_t workspace_bytes,
+                             int32_t training, int32_t batch_stats, cudaStream_t stream);
 /* autograd of the above (replaces torch autograd over src/conv_tasnet.py:45-60):
  * d_est [M,C,T] -> grads (flat, same layout as params).  accumulate == 0 overwrites grads. */
 int32_t ctn_model_backward(const ctn_config* cfg, const float* params, const float* mixture,

@@ -58,6 +58,11 @@ PAPER = Config()
 # --------------------------------------------------------------------------------------
 # parameter inventory (state_dict contract; src/conv_tasnet.py:150-278)
 # --------------------------------------------------------------------------------------
+def is_batch_norm(cfg: Config) -> bool:
+    """chose_norm (src/conv_tasnet.py:298-309): every norm_type other than gLN / cLN builds nn.BatchNorm1d."""
+    return cfg.norm_type not in ("gLN", "cLN")
+
+
 def param_spec(cfg: Config) -> List[Tuple[str, Tuple[int, ...]]]:
     """(name, shape) in the order `ConvTasNet(...).state_dict()` yields them."""
     spec = [("encoder.conv1d_U.weight", (cfg.N, 1, cfg.L)),
@@ -67,18 +72,23 @@ def param_spec(cfg: Config) -> List[Tuple[str, Tuple[int, ...]]]:
     # Chomp1d sits at index 1 of DepthwiseSeparableConv.net in the causal variant
     # (src/conv_tasnet.py:264-269), shifting the later indices by one.
     sh = 1 if cfg.causal else 0
+
+    def norm_entries(prefix):
+        if is_batch_norm(cfg):  # nn.BatchNorm1d(H) parameters and buffers, in state_dict order (:306-309)
+            return [(prefix + "weight", (cfg.H,)), (prefix + "bias", (cfg.H,)), (prefix + "running_mean", (cfg.H,)),
+                    (prefix + "running_var", (cfg.H,)), (prefix + "num_batches_tracked", ())]
+        return [(prefix + "gamma", (1, cfg.H, 1)), (prefix + "beta", (1, cfg.H, 1))]
+
     for r in range(cfg.R):
         for x in range(cfg.X):
             p = f"separator.network.2.{r}.{x}.net."
             spec += [(p + "0.weight", (cfg.H, cfg.B, 1)),
-                     (p + "1.weight", (1,)),
-                     (p + "2.gamma", (1, cfg.H, 1)),
-                     (p + "2.beta", (1, cfg.H, 1)),
-                     (p + "3.net.0.weight", (cfg.H, 1, cfg.P)),
-                     (p + f"3.net.{1 + sh}.weight", (1,)),
-                     (p + f"3.net.{2 + sh}.gamma", (1, cfg.H, 1)),
-                     (p + f"3.net.{2 + sh}.beta", (1, cfg.H, 1)),
-                     (p + f"3.net.{3 + sh}.weight", (cfg.B, cfg.H, 1))]
+                     (p + "1.weight", (1,))]
+            spec += norm_entries(p + "2.")
+            spec += [(p + "3.net.0.weight", (cfg.H, 1, cfg.P)),
+                     (p + f"3.net.{1 + sh}.weight", (1,))]
+            spec += norm_entries(p + f"3.net.{2 + sh}.")
+            spec += [(p + f"3.net.{3 + sh}.weight", (cfg.B, cfg.H, 1))]
     spec += [("separator.network.3.weight", (cfg.C * cfg.N, cfg.B, 1)),
              ("decoder.basis_signals.weight", (cfg.L, cfg.N))]
     return spec
@@ -91,7 +101,14 @@ def init_state_dict(cfg: Config, seed: int = 0, dtype=torch.float32) -> Dict[str
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for name, shape in param_spec(cfg):
-        if len(shape) == 1:
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "num_batches_tracked":
+            sd[name] = torch.zeros((), dtype=torch.int64)
+        elif leaf in ("running_mean", "bias") and len(shape) == 1:
+            sd[name] = torch.zeros(shape, dtype=dtype)
+        elif leaf == "running_var" or (leaf == "weight" and len(shape) == 1 and shape[0] != 1):
+            sd[name] = torch.ones(shape, dtype=dtype)  # BatchNorm1d defaults (1-D: not touched by the xavier loop, :41-43)
+        elif len(shape) == 1:
             sd[name] = torch.full(shape, 0.25, dtype=dtype)
         else:
             rf = 1
@@ -132,38 +149,59 @@ def global_layer_norm(y, gamma, beta):
     return gamma * (y - mean) / torch.pow(var + EPS, 0.5) + beta
 
 
-def _norm(cfg: Config, y, gamma, beta):
+def batch_norm(y, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm1d(C) on [M, C, K] (src/conv_tasnet.py:306-309; torch defaults eps 1e-5, momentum 0.1, affine):
+    training: statistics over (M, K) per channel, biased variance to normalise, running statistics updated in place
+    with the unbiased one; evaluation: the running statistics."""
+    if training:
+        mean = y.mean(dim=(0, 2))
+        var = y.var(dim=(0, 2), unbiased=False)
+        n = y.shape[0] * y.shape[2]
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(momentum * mean.to(running_mean.dtype))
+            running_var.mul_(1 - momentum).add_(momentum * (var * (n / max(n - 1, 1))).to(running_var.dtype))
+    else:
+        mean, var = running_mean.to(y.dtype), running_var.to(y.dtype)
+    xhat = (y - mean.view(1, -1, 1)) / torch.sqrt(var.view(1, -1, 1) + eps)
+    return xhat * weight.view(1, -1, 1) + bias.view(1, -1, 1)
+
+
+def _norm(cfg: Config, sd, prefix: str, y, training: bool):
+    """the norm chose_norm built at `prefix` (src/conv_tasnet.py:298-309)"""
     if cfg.norm_type == "gLN":
-        return global_layer_norm(y, gamma, beta)
+        return global_layer_norm(y, sd[prefix + "gamma"], sd[prefix + "beta"])
     if cfg.norm_type == "cLN":
-        return channelwise_layer_norm(y, gamma, beta)
-    raise NotImplementedError("BatchNorm branch (src/conv_tasnet.py:306-309) is outside the hot path")
+        return channelwise_layer_norm(y, sd[prefix + "gamma"], sd[prefix + "beta"])
+    if training:
+        sd[prefix + "num_batches_tracked"] += 1
+    return batch_norm(y, sd[prefix + "weight"], sd[prefix + "bias"], sd[prefix + "running_mean"],
+                      sd[prefix + "running_var"], training)
 
 
-def temporal_block(cfg: Config, sd, prefix: str, x: torch.Tensor, dilation: int) -> torch.Tensor:
+def temporal_block(cfg: Config, sd, prefix: str, x: torch.Tensor, dilation: int, training: bool = True) -> torch.Tensor:
     """x + pointwise(norm(prelu(depthwise(norm(prelu(conv1x1(x))))))) (src/conv_tasnet.py:223-243,253-278)."""
     sh = 1 if cfg.causal else 0
     pad = (cfg.P - 1) * dilation if cfg.causal else (cfg.P - 1) * dilation // 2  # :182
     y = F.conv1d(x, sd[prefix + "0.weight"])
     y = F.prelu(y, sd[prefix + "1.weight"])
-    y = _norm(cfg, y, sd[prefix + "2.gamma"], sd[prefix + "2.beta"])
+    y = _norm(cfg, sd, prefix + "2.", y, training)
     y = F.conv1d(y, sd[prefix + "3.net.0.weight"], padding=pad, dilation=dilation, groups=cfg.H)
     if cfg.causal:
         y = y[:, :, :-pad].contiguous()  # Chomp1d, :295
     y = F.prelu(y, sd[prefix + f"3.net.{1 + sh}.weight"])
-    y = _norm(cfg, y, sd[prefix + f"3.net.{2 + sh}.gamma"], sd[prefix + f"3.net.{2 + sh}.beta"])
+    y = _norm(cfg, sd, prefix + f"3.net.{2 + sh}.", y, training)
     y = F.conv1d(y, sd[prefix + f"3.net.{3 + sh}.weight"])
     return y + x  # no output ReLU (:243)
 
 
-def separator(cfg: Config, sd, mixture_w: torch.Tensor) -> torch.Tensor:
+def separator(cfg: Config, sd, mixture_w: torch.Tensor, training: bool = True) -> torch.Tensor:
     """[M,N,K] -> mask [M,C,N,K] (src/conv_tasnet.py:172-214).  First norm is always cLN (:172)."""
     M, N, K = mixture_w.shape
     y = channelwise_layer_norm(mixture_w, sd["separator.network.0.gamma"], sd["separator.network.0.beta"])
     y = F.conv1d(y, sd["separator.network.1.weight"])
     for r in range(cfg.R):
         for x in range(cfg.X):
-            y = temporal_block(cfg, sd, f"separator.network.2.{r}.{x}.net.", y, 2 ** x)  # :181
+            y = temporal_block(cfg, sd, f"separator.network.2.{r}.{x}.net.", y, 2 ** x, training)  # :181
     score = F.conv1d(y, sd["separator.network.3.weight"]).view(M, cfg.C, N, K)  # channel = c*N + n (:208)
     if cfg.mask_nonlinear == "softmax":
         return F.softmax(score, dim=1)
@@ -203,10 +241,12 @@ def decoder(mixture_w, est_mask, V, L: int):
     return overlap_and_add_fast(frames, L // 2)
 
 
-def forward(cfg: Config, sd, mixture: torch.Tensor) -> torch.Tensor:
-    """ConvTasNet.forward (src/conv_tasnet.py:45-60): [M,T] -> [M,C,T], right-padded with zeros."""
+def forward(cfg: Config, sd, mixture: torch.Tensor, training: bool = True) -> torch.Tensor:
+    """ConvTasNet.forward (src/conv_tasnet.py:45-60): [M,T] -> [M,C,T], right-padded with zeros.
+    `training` is nn.Module.training (default True, like a freshly built module); it only matters for the BatchNorm
+    branch, whose running statistics inside `sd` are then updated in place."""
     w = encoder(mixture, sd["encoder.conv1d_U.weight"])
-    mask = separator(cfg, sd, w)
+    mask = separator(cfg, sd, w, training)
     est = decoder(w, mask, sd["decoder.basis_signals.weight"], cfg.L)
     return F.pad(est, (0, mixture.shape[-1] - est.shape[-1]))
 
@@ -284,12 +324,18 @@ def synthetic_batch(M: int, T: int, C: int, L: int, seed: int, dtype=torch.float
     return mix, src, lengths
 
 
-def train_step_grads(cfg: Config, sd, mixture, source, lengths):
-    """forward + cal_loss + backward through autograd; returns (loss, est (masked), grads by name)."""
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    est = forward(cfg, params, mixture)
+def is_buffer(name: str) -> bool:
+    """BatchNorm1d buffers inside a state_dict (no gradient; the running statistics are updated in place)"""
+    return name.rsplit(".", 1)[-1] in ("running_mean", "running_var", "num_batches_tracked")
+
+
+def train_step_grads(cfg: Config, sd, mixture, source, lengths, training: bool = True):
+    """forward + cal_loss + backward through autograd; returns (loss, est (masked), grads by name).
+    BatchNorm buffers in `sd` are used (and, when `training`, updated) in place, like the module's."""
+    params = {k: (v if is_buffer(k) else v.detach().clone().requires_grad_(True)) for k, v in sd.items()}
+    est = forward(cfg, params, mixture, training)
     loss, max_snr, est_masked, reordered = cal_loss(source, est, lengths)
-    names = list(params)
+    names = [k for k in params if not is_buffer(k)]
     grads = torch.autograd.grad(loss, [params[k] for k in names])
     return loss.detach(), est_masked.detach(), dict(zip(names, grads)), max_snr.detach(), reordered.detach()
 

@@ -55,6 +55,33 @@ def test_param_layout_matches_state_dict(lib, causal):
     assert seen == total
 
 
+def test_batchnorm_layout_and_seeded_init(lib):
+    """BN branch: weight / bias sit where gamma / beta do; running statistics travel in norm_state; a seeded constructor
+    call yields the reference's state_dict (keys, shapes, values; fixture values from tests/golden/model_bn.npz keys)."""
+    import torch
+    from conv_tasnet_b200 import ConvTasNet
+    cfg = O.Config(N=16, L=8, B=8, H=16, P=3, X=3, R=2, C=2, norm_type="BN")
+    c = lib.make_config(**cfg.as_dict())
+    L = lib.lib()
+    assert c.norm_type == 2
+    assert L.ctn_norm_state_floats(ctypes.byref(c)) == cfg.R * cfg.X * 4 * cfg.H
+    assert L.ctn_norm_state_floats(ctypes.byref(lib.make_config(**O.PAPER.as_dict()))) == 0
+    spec = [(k, s) for k, s in O.param_spec(cfg) if not O.is_buffer(k)]
+    n = L.ctn_param_tensors(ctypes.byref(c))
+    assert n == len(spec)
+    offs, nums = (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)()
+    assert L.ctn_param_layout(ctypes.byref(c), offs, nums, n) == 0
+    assert [int(x) for x in nums] == [int(np.prod(s)) for _, s in spec]
+    torch.manual_seed(0)
+    m = ConvTasNet(**cfg.as_dict())
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == O.param_spec(cfg)
+    sd = O.init_state_dict(cfg)
+    for k, v in m.state_dict().items():  # BatchNorm1d defaults: weight 1, bias 0, running (0, 1), counter 0
+        if k.split(".")[-1] in ("bias", "running_mean", "running_var", "num_batches_tracked") or \
+                (k.endswith("weight") and v.dim() == 1 and v.numel() > 1):
+            assert torch.equal(v, sd[k]), k
+
+
 def test_geometry_and_validation(lib):
     L = lib.lib()
     c = lib.make_config(**O.PAPER.as_dict())
@@ -112,8 +139,8 @@ def test_no_cpu_fallback():
         cal_loss(torch.zeros(1, 2, 8), torch.zeros(1, 2, 8), torch.tensor([8]))
     with pytest.raises(RuntimeError, match="CUDA"):
         overlap_and_add(torch.zeros(1, 3, 4), 2)
-    with pytest.raises(NotImplementedError):
-        ConvTasNet(**dict(cfgd, norm_type="BN"))
+    bn = ConvTasNet(**dict(cfgd, norm_type="BN"))  # the BatchNorm fall-through of chose_norm (src/conv_tasnet.py:306)
+    assert bn._cfg.norm_type == 2 and len(bn._bns) == 2 * cfgd["R"] * cfgd["X"]
 
 
 def test_remove_pad_matches_reference_semantics():

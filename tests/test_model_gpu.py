@@ -131,6 +131,7 @@ def test_paper_config2_training_step_against_fp64_truth():
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=3, norm_type="gLN", causal=False, mask_nonlinear="relu"), 2, 12000),
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="cLN", causal=True, mask_nonlinear="relu"), 2, 12000),
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="softmax"), 2, 12000),
+    (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="BN", causal=False, mask_nonlinear="relu"), 2, 12000),
 ])
 def test_paper_width_against_fp64_oracle(cfgd, M, T):
     """Full-width variants (C=3 six-permutation PIT, causal cLN, softmax mask) against the CPU oracle run in fp64 on
@@ -142,9 +143,10 @@ def test_paper_width_against_fp64_oracle(cfgd, M, T):
     model.load_state_dict(sd)
     model = model.cuda().train()
     mix, src, lens = O.synthetic_batch(M, T, cfg.C, cfg.L, 1234)
-    sd64 = {k: v.double() for k, v in sd.items()}
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
     loss_o, est_o, grads_o, max_snr_o, reord_o = O.train_step_grads(cfg, sd64, mix.double(), src.double(), lens)
-    _, _, grads_32, _, _ = O.train_step_grads(cfg, sd, mix, src, lens)  # the reference's own fp32 noise, for calibration
+    sd32 = {k: v.clone() for k, v in sd.items()}  # (BatchNorm buffers are updated in place: keep `sd` pristine)
+    _, _, grads_32, _, _ = O.train_step_grads(cfg, sd32, mix, src, lens)  # the reference's own fp32 noise, for calibration
     est = model(mix.cuda())
     loss, max_snr, est_m, reord = cal_loss(src.cuda(), est, lens)
     loss.backward()
@@ -163,6 +165,50 @@ def test_paper_width_against_fp64_oracle(cfgd, M, T):
     want = torch.stack([grads_o[k].double().view(()) for k in sc])
     ref = torch.stack([grads_32[k].double().view(()) for k in sc])
     assert rel_l2(mine, want) < grad_tolerance(rel_l2(ref, want)), (rel_l2(mine, want), rel_l2(ref, want))
+    for k, b in model.named_buffers():  # BatchNorm running statistics after one training step
+        assert rel_err(b.cpu(), sd64[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["bn", "bn_causal_c3"])
+def test_batchnorm_branch_matches_reference_golden(name):
+    """norm_type other than gLN / cLN -> nn.BatchNorm1d (src/conv_tasnet.py:306-309), against vectors produced by the
+    reference (tests/golden/make_golden_bn.py): evaluation mode uses (and leaves alone) the running statistics,
+    training mode uses the batch statistics, differentiates through them and updates the running statistics."""
+    from conv_tasnet_b200 import cal_loss
+    cfgd, sd, z = golden_model(name)
+    model = build(cfgd, sd)
+    mix = torch.from_numpy(z["mixture"]).cuda()
+    src = torch.from_numpy(z["source"]).cuda()
+    lens = torch.from_numpy(z["lengths"])
+
+    def step(prefix_est, prefix_loss, prefix_grad):
+        est = model(mix)
+        assert rel_err(est.detach().cpu(), z[prefix_est]) < 1e-4
+        loss, max_snr, _, _ = cal_loss(src, est, lens)
+        assert abs(loss.item() - float(z[prefix_loss])) < 0.01
+        model.zero_grad()
+        loss.backward()
+        errs = {k: rel_err(p.grad.cpu(), z[prefix_grad + k]) for k, p in model.named_parameters()}
+        assert max(errs.values()) < 1e-3, max(errs.items(), key=lambda t: t[1])
+
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model(mix).cpu(), z["eval_est_source"]) < 1e-4
+    step("eval_est_source", "eval_loss", "ge:")
+    for k, b in model.named_buffers():
+        assert torch.equal(b.cpu(), sd[k]), k  # evaluation leaves the buffers alone
+    model.train()
+    step("est_source", "loss", "g:")
+    for k, b in model.named_buffers():
+        if k.endswith("num_batches_tracked"):
+            assert b.item() == 1
+        else:
+            assert rel_err(b.cpu(), z["after:" + k]) < 1e-5, k
+    # the state_dict round-trips into a fresh model (keys and shapes are the reference's)
+    again = build(cfgd, {k: v.cpu() for k, v in model.state_dict().items()}).eval()
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(again(mix), model(mix))
 
 
 def test_full_size_properties_causal_cln_batch32():
@@ -228,8 +274,6 @@ def test_error_behaviour_and_no_cpu_fallback():
         m(torch.zeros(1, 403))
     with pytest.raises(RuntimeError, match="CUDA"):
         cal_loss(torch.zeros(1, 2, 8), torch.zeros(1, 2, 8), torch.tensor([8]))
-    with pytest.raises(NotImplementedError):
-        ConvTasNet(**dict(cfgd, norm_type="BN"))
     with pytest.raises(TypeError):
         cal_loss(torch.zeros(1, 2, 8).cuda().double(), torch.zeros(1, 2, 8).cuda().double(), torch.tensor([8]))
 

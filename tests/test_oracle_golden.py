@@ -100,3 +100,31 @@ def test_paper_config_forward_matches_reference_samples():
     assert names == [k for k, _ in O.param_spec(cfg)]
     assert sum(int(np.prod(s)) for _, s in O.param_spec(cfg)) == 8710720  # SURVEY §8 [verified]
     assert O.n_frames(32000, 20) == 3199 and O.n_frames(480000, 20) == 47999
+
+
+@pytest.mark.parametrize("name", ["bn", "bn_causal_c3"])
+def test_batchnorm_branch_against_reference(name):
+    """norm_type other than gLN / cLN -> nn.BatchNorm1d (src/conv_tasnet.py:306-309): evaluation mode (running
+    statistics), training mode (batch statistics) and the running-statistics update, vs tests/golden/make_golden_bn.py"""
+    cfgd, sd, z = golden_model(name)
+    cfg = O.Config(**cfgd)
+    assert [k for k, _ in O.param_spec(cfg)] == list(sd.keys())
+    assert all(tuple(sd[k].shape) == s for k, s in O.param_spec(cfg))
+    mix, src, lens = (torch.from_numpy(z[k]) for k in ("mixture", "source", "lengths"))
+    sd_e = {k: v.clone() for k, v in sd.items()}
+    assert rel_err(O.forward(cfg, sd_e, mix, training=False), z["eval_est_source"]) < 1e-5
+    loss, _, grads, max_snr, _ = O.train_step_grads(cfg, sd_e, mix, src, lens, training=False)
+    assert abs(loss.item() - float(z["eval_loss"])) < 1e-3
+    assert all(torch.equal(sd_e[k], sd[k]) for k in sd if O.is_buffer(k))  # evaluation leaves the buffers alone
+    errs = sorted(rel_err(g, z["ge:" + k]) for k, g in grads.items())
+    assert errs[len(errs) // 2] < 1e-4 and errs[-1] < 5e-3  # isolated PReLU-kink outliers, see conftest
+    sd_t = {k: v.clone() for k, v in sd.items()}
+    est = O.forward(cfg, {k: v.clone() for k, v in sd.items()}, mix, training=True)
+    assert rel_err(est, z["est_source"]) < 1e-5
+    loss, _, grads, max_snr, _ = O.train_step_grads(cfg, sd_t, mix, src, lens, training=True)
+    assert abs(loss.item() - float(z["loss"])) < 1e-3
+    for k, g in grads.items():
+        assert rel_err(g, z["g:" + k]) < 1e-3, k
+    for k in sd:
+        if O.is_buffer(k):
+            assert rel_err(sd_t[k], z["after:" + k]) < 1e-5, k
