@@ -316,13 +316,15 @@ def test_torch_adam_training_loop_reduces_loss_like_solver():
     assert losses[-1] < losses[0] - 1.0, losses
 
 
-def test_fused_adam_and_graphed_step_match_torch_adam_eager():
+@pytest.mark.parametrize("name", ["gln", "bn"])
+def test_fused_adam_and_graphed_step_match_torch_adam_eager(name):
     """The fused step tail (clip + Adam on the flat buffers) and the CUDA-graph replay of the whole step follow the
-    reference's solver step (torch.optim.Adam + clip_grad_norm_, solver.py:192-196) parameter for parameter."""
+    reference's solver step (torch.optim.Adam + clip_grad_norm_, solver.py:192-196) parameter for parameter
+    (BatchNorm: the running statistics and batch counters advance inside the graph as well)."""
     from conv_tasnet_b200 import ConvTasNet, cal_loss
     from conv_tasnet_b200.graph import GraphedInference, GraphedTrainStep
     from conv_tasnet_b200.optim import FusedAdam
-    cfgd, sd, z = golden_model("gln")
+    cfgd, sd, z = golden_model(name)
     mix, src = torch.from_numpy(z["mixture"]).cuda(), torch.from_numpy(z["source"]).cuda()
     lens = torch.from_numpy(z["lengths"]).cuda()
     ref = build(cfgd, sd).train()
@@ -357,6 +359,8 @@ def test_fused_adam_and_graphed_step_match_torch_adam_eager():
         assert max(abs(a - b) for a, b in zip(losses, losses_ref)) < 2e-3, (graphed, losses, losses_ref)
         for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
             assert rel_err(p.detach().cpu(), q.detach().cpu()) < 2e-3, (graphed, k)
+        for (k, p), (_, q) in zip(model.named_buffers(), ref.named_buffers()):
+            assert rel_err(p.cpu(), q.cpu()) < 2e-3 and (p.is_floating_point() or p.item() == 4), (graphed, k)
     infer = GraphedInference(model.eval())
     with torch.no_grad():
         want = model(mix)
