@@ -6,6 +6,7 @@ Mirrors the reference's module layout for the path it replaces:
     conv_tasnet_b200.utils          <->  src/utils.py          (overlap_and_add, remove_pad)
     conv_tasnet_b200.data_parallel  <->  nn.DataParallel use in src/train.py:83-85 (one process per GPU + NCCL)
     conv_tasnet_b200.optim          <->  the clip + Adam tail of src/solver.py:192-196
+    conv_tasnet_b200.data           <->  _collate_fn / pad_list + .cuda() of src/data.py:159-183,322-331 (device-side)
 All compute goes through libctn_b200.so (hand-written CUDA behind the C ABI of include/ctn_b200.h).
 """
 from .conv_tasnet import ConvTasNet  # noqa: F401

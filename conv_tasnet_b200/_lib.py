@@ -30,6 +30,8 @@ SIGNATURES = {
     "ctn_grad_bucket": (c_i32, [_P, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "ctn_model_forward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "ctn_norm_state_floats": (c_i64, [_P]),
+    "ctn_assemble_batch": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ctn_pack_valid": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ctn_model_forward_bn": (c_i32, [_P, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "ctn_model_backward": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "ctn_model_backward_stage": (c_i32, [_P, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),

@@ -30,6 +30,9 @@ int run_clip_grad_norm(float*, int64_t, float, float*, void*, cudaStream_t);
 int run_adam_step(float*, const float*, float*, float*, int64_t, float, float, float, float, float, int64_t*,
                   cudaStream_t);
 
+int run_assemble_batch(const float*, const float*, const int64_t*, int, int, int, float*, float*, int64_t*, cudaStream_t);
+int run_pack_valid(const float*, const int64_t*, const int64_t*, int, int, int, float*, cudaStream_t);
+
 static NormStats make_stats(const double* gln_acc, const float* rowstat, int K, int Ch) {
   NormStats st;
   st.acc = gln_acc;
@@ -44,6 +47,19 @@ using namespace ctn;
 extern "C" {
 
 int64_t ctn_pit_workspace_bytes(int32_t B, int32_t C) { return pit_workspace_bytes(B, C); }
+
+int32_t ctn_assemble_batch(const float* packed_mix, const float* packed_src, const int64_t* offsets, int32_t B, int32_t C,
+                           int32_t T, float* padded_mixture, float* padded_source, int64_t* lengths,
+                           cudaStream_t stream) {
+  CTN_REQUIRE(packed_mix && offsets && padded_mixture && lengths, "assemble_batch: null pointer");
+  return run_assemble_batch(packed_mix, packed_src, offsets, B, C, T, padded_mixture, padded_source, lengths, stream);
+}
+
+int32_t ctn_pack_valid(const float* inputs, const int64_t* lengths, const int64_t* out_offsets, int32_t B, int32_t C,
+                       int32_t T, float* packed, cudaStream_t stream) {
+  CTN_REQUIRE(inputs && lengths && out_offsets && packed, "pack_valid: null pointer");
+  return run_pack_valid(inputs, lengths, out_offsets, B, C, T, packed, stream);
+}
 
 int32_t ctn_pit_forward(const float* source, float* est, const int64_t* lengths, int32_t B, int32_t C, int32_t T,
                         float* loss, float* max_snr, int64_t* idx, float* reorder, float* coef, void* pit_ws,

@@ -36,12 +36,34 @@ def remove_pad(inputs, inputs_lengths):
         inputs_lengths: torch.Tensor, [B]
     Returns:
         results: a list containing B items, each item is [C, T], T varies
-    (src/utils.py:50-67; one device->host copy for the whole batch instead of one per item)
+    (src/utils.py:50-67).  CUDA inputs: one kernel packs the valid samples of the whole batch (ctn_pack_valid) and ONE
+    device->host copy brings exactly those back, instead of one slice + copy per item; CPU inputs are sliced in numpy.
     """
+    if inputs.dim() not in (2, 3):
+        return []
+    T = inputs.shape[-1]
+    lengths = [min(max(int(n), 0), T) for n in torch.as_tensor(inputs_lengths).tolist()][:inputs.shape[0]]
+    C = inputs.shape[1] if inputs.dim() == 3 else 1
+    if inputs.is_cuda and inputs.dtype == torch.float32 and len(lengths) > 0 and sum(lengths) > 0:
+        B = len(lengths)
+        offs = [0]
+        for n in lengths:
+            offs.append(offs[-1] + n)
+        with torch.cuda.device(inputs.device):
+            meta = torch.tensor(lengths + offs[:-1], dtype=torch.int64).pin_memory().to(inputs.device, non_blocking=True)
+            packed = torch.empty(offs[-1] * C, dtype=torch.float32, device=inputs.device)
+            _lib.check(_lib.lib().ctn_pack_valid(_lib.ptr(inputs.detach().contiguous()), meta.data_ptr(),
+                                                 meta.data_ptr() + 8 * B, B, C, T, _lib.ptr(packed), _lib.stream()))
+            host = torch.empty(packed.shape, dtype=torch.float32).pin_memory()
+            host.copy_(packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        flat = host.numpy()
+        out = []
+        for b, n in enumerate(lengths):
+            item = flat[offs[b] * C:offs[b + 1] * C].copy()
+            out.append(item.reshape(C, n) if inputs.dim() == 3 else item)
+        return out
     host = inputs.detach().cpu().numpy()
-    lengths = [int(n) for n in torch.as_tensor(inputs_lengths).tolist()]
     if inputs.dim() == 3:
         return [host[b, :, :n].reshape(host.shape[1], -1).copy() for b, n in enumerate(lengths)]
-    if inputs.dim() == 2:
-        return [host[b, :n].reshape(-1).copy() for b, n in enumerate(lengths)]
-    return []
+    return [host[b, :n].reshape(-1).copy() for b, n in enumerate(lengths)]

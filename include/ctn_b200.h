@@ -112,6 +112,20 @@ int32_t ctn_reorder_source(const float* source, const int64_t* idx, int32_t B, i
 int32_t ctn_overlap_and_add(const float* signal, int64_t outer, int32_t frames, int32_t frame_length,
                             int32_t frame_step, float* out, cudaStream_t stream);
 
+/* ---- batch assembly ---------------------------------------------------------- */
+/* _collate_fn + pad_list + .cuda() (src/data.py:159-183,322-331; src/solver.py:184-187) on the device.
+ * packed_mix: the B mixtures back to back (offsets[b] .. offsets[b+1] samples, offsets [B+1] on the device);
+ * packed_src: the B sources back to back in the loader's [T_b, C] layout, or NULL (evaluation collate, :239-260).
+ * -> padded_mixture [B,T] and padded_source [B,C,T] zero padded (pad_value 0), lengths [B] (T >= every length). */
+int32_t ctn_assemble_batch(const float* packed_mix, const float* packed_src, const int64_t* offsets,
+                           int32_t B, int32_t C, int32_t T, float* padded_mixture, float* padded_source,
+                           int64_t* lengths, cudaStream_t stream);
+/* utils.remove_pad (src/utils.py:50-67) without the per-item copies: item b of inputs [B,C,T] (C = 1 for [B,T]) is
+ * written as a dense [C, lengths[b]] block starting at float out_offsets[b] * C of `packed` (out_offsets = exclusive
+ * prefix sum of the lengths); the caller then does ONE device->host copy of `packed`. */
+int32_t ctn_pack_valid(const float* inputs, const int64_t* lengths, const int64_t* out_offsets, int32_t B,
+                       int32_t C, int32_t T, float* packed, cudaStream_t stream);
+
 /* ---- step tail (solver.py:192-196: clip_grad_norm_ + Adam) on the flat buffers ----------- */
 /* total L2 norm -> norm_out[0]; grads *= min(1, max_norm/(norm+1e-6)) like torch clip_grad_norm_.
  * scratch: >= 8 * 1024 bytes */
