@@ -22,6 +22,7 @@ SIGNATURES = {
     "ctn_version": (c_i32, []),
     "ctn_last_error": (ctypes.c_char_p, []),
     "ctn_launch_count": (c_i64, []),
+    "ctn_timing_report": (c_i32, [c_i32]),
     "ctn_param_tensors": (c_i32, [_P]),
     "ctn_param_floats": (c_i64, [_P]),
     "ctn_param_layout": (c_i32, [_P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32]),

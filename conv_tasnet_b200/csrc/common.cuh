@@ -50,6 +50,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+// CTN_TIMING=1 (debug): every launch is followed by an event on its stream; ctn_timing_report() prints per-kernel totals
+// measured in place (realistic cache state, unlike a profiler's cold-cache replays).  Off: one predictable branch.
+void timing_note_stream(cudaStream_t s);
 
 template <typename... KArgs, typename... Args>
 static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -65,6 +68,7 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors are picked up by check_launch()
+  timing_note_stream(stream);
 }
 
 // ---- normalisation statistics -----------------------------------------------------------

@@ -1002,7 +1002,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
     else return launch_gemm_simt(g, s);
   }
 #undef CTN_TC_LAUNCH
-  return check_launch("tc_gemm_kernel");
+  return check_launch(g.tf32 ? (g.O > g.Kd ? "tc_gemm_kernel<tf32> up" : "tc_gemm_kernel<tf32> down")
+                             : (g.O > g.Kd ? "tc_gemm_kernel<bf16> up" : "tc_gemm_kernel<bf16> down"));
 }
 
 bool tc_wgrad_eligible(const WgradArgs& a) {

@@ -28,8 +28,38 @@ bool pdl_enabled() {
   return v == 1;
 }
 static unsigned long long g_launches = 0;  // kernels launched through this library (bench.py's gpu_launches)
+
+// ---- CTN_TIMING=1: in-place per-kernel timing (debug) ------------------------------------------
+struct TimingRec {
+  const char* name;
+  cudaEvent_t ev;
+};
+static bool timing_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTN_TIMING");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static TimingRec* g_trec = nullptr;
+static int g_ntrec = 0, g_trec_cap = 0;
+static thread_local cudaStream_t g_tstream = nullptr;
+void timing_note_stream(cudaStream_t s) { g_tstream = s; }
+static void timing_mark(const char* what) {
+  if (g_ntrec == g_trec_cap) {
+    g_trec_cap = g_trec_cap ? 2 * g_trec_cap : 4096;
+    g_trec = (TimingRec*)realloc(g_trec, sizeof(TimingRec) * g_trec_cap);
+  }
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, g_tstream);
+  g_trec[g_ntrec++] = TimingRec{what, ev};
+}
+
 int check_launch(const char* what) {
   __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
+  if (timing_enabled()) timing_mark(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -641,6 +671,37 @@ using namespace ctn;
 extern "C" {
 
 int32_t ctn_version(void) { return 100; }
+
+// debug: per-kernel time between consecutive launch events recorded since the last report (CTN_TIMING=1); a launch's
+// interval starts at the previous launch's event, so memsets / gaps are charged to the kernel that follows them
+int32_t ctn_timing_report(int32_t reset_only) {
+  if (!timing_enabled()) return 0;
+  cudaDeviceSynchronize();
+  if (!reset_only && g_ntrec > 1) {
+    struct Agg { const char* name; double ms; int n; };
+    Agg agg[64];
+    int na = 0;
+    double total = 0.0;
+    for (int i = 1; i < g_ntrec; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, g_trec[i - 1].ev, g_trec[i].ev) != cudaSuccess) continue;
+      int j = 0;
+      for (; j < na; ++j)
+        if (strcmp(agg[j].name, g_trec[i].name) == 0) break;
+      if (j == na && na < 64) agg[na++] = Agg{g_trec[i].name, 0.0, 0};
+      if (j < 64) { agg[j].ms += ms; agg[j].n += 1; }
+      total += ms;
+    }
+    printf("ctn timing: %d launches, %.3f ms\n", g_ntrec - 1, total);
+    for (int j = 0; j < na; ++j)
+      printf("  %-32s n=%5d  total %8.3f ms  avg %7.2f us  %5.1f %%\n", agg[j].name, agg[j].n, agg[j].ms,
+             1000.0 * agg[j].ms / agg[j].n, 100.0 * agg[j].ms / total);
+    fflush(stdout);
+  }
+  for (int i = 0; i < g_ntrec; ++i) cudaEventDestroy(g_trec[i].ev);
+  g_ntrec = 0;
+  return 0;
+}
 int64_t ctn_launch_count(void) { return (int64_t)__atomic_load_n(&ctn::g_launches, __ATOMIC_RELAXED); }
 const char* ctn_last_error(void) { return ctn::last_error(); }
 

@@ -41,6 +41,9 @@ int32_t ctn_version(void);
 const char* ctn_last_error(void);
 /* number of CUDA kernels this library has launched in this process (monotonic; for bench.py's gpu_launches) */
 int64_t ctn_launch_count(void);
+/* debug (CTN_TIMING=1 in the environment, eager launches only): prints per-kernel time measured in place between the
+ * launches recorded since the previous call, then clears the records; reset_only != 0 just clears.  No-op otherwise. */
+int32_t ctn_timing_report(int32_t reset_only);
 
 /* ---- parameter / workspace geometry (host only, no GPU needed) -------------------------- */
 /* number of tensors in state_dict order (src/conv_tasnet.py state_dict(): 4 + 9*R*X + 2) */
