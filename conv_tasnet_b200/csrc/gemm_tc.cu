@@ -644,6 +644,7 @@ struct TcWgradArgs {
   NormStats st;
 };
 
+constexpr int WG_STAT_CACHE = 16;  // samples whose (mean, rstd) a CTA caches; more fall back to load_stats per row
 template <int NI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
   pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
@@ -658,6 +659,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
   uint64_t* empty = full + WSTAGES;
   uint64_t* tmem_full = empty + WSTAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float2* s_wst = reinterpret_cast<float2*>(tail + 128);  // [WG_STAT_CACHE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o0 = blockIdx.x * BM, i0 = blockIdx.y * NI;
@@ -723,6 +725,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         gam[i] = norm ? __ldg(a.gamma + i0 + xc * 8 + i) : 1.f;
         bet[i] = norm ? __ldg(a.beta + i0 + xc * 8 + i) : 0.f;
       }
+      // per-sample (gLN / identity) statistics of the samples this f-chunk touches, derived ONCE per CTA: load_stats is
+      // fp64 (mean, rsqrt of the variance) and used to run per row per thread (+11 us per launch, measured in place)
+      const bool per_sample = norm && a.st.row == nullptr;
+      const int m_lo = (int)((uint32_t)fb / (uint32_t)a.K);
+      if (per_sample) {
+        if (t < WG_STAT_CACHE && (int64_t)(m_lo + t) * a.K < fe) {
+          float mu, r;
+          load_stats(a.st, m_lo + t, 0, mu, r);
+          s_wst[t] = make_float2(mu, r);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       for (int kb = grp; kb < nkb; kb += 2) {
         const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
         const int64_t fk = fb + (int64_t)kb * WK;
@@ -769,7 +783,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
             }
             if (norm) {
               float mu, r;
-              load_stats(a.st, (int)(f / a.K), f, mu, r);
+              const int m = (int)((uint32_t)f / (uint32_t)a.K);
+              if (per_sample && m - m_lo < WG_STAT_CACHE) {
+                const float2 v = s_wst[m - m_lo];
+                mu = v.x;
+                r = v.y;
+              } else {
+                load_stats(a.st, m, f, mu, r);
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] = gam[i] * (x[i] - mu) * r + bet[i];
             }
@@ -1031,13 +1052,13 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
     attr_mask |= 1ull << (dev & 63);
   }
   if (ni == 256) {
-    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128;
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128 + 8 * WG_STAT_CACHE;
     launch_kernel(tc_wgrad_kernel<256>, grid, TC_THREADS, smem, s, a);
   } else {
-    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128;
+    const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128 + 8 * WG_STAT_CACHE;
     launch_kernel(tc_wgrad_kernel<128>, grid, TC_THREADS, smem, s, a);
   }
-  return check_launch("tc_wgrad_kernel");
+  return check_launch(w.gamma != nullptr ? "tc_wgrad_kernel (norm prologue)" : "tc_wgrad_kernel (plain)");
 }
 
 int run_split_planes_tf32(const float* src, int64_t n, int nb, int64_t src_stride, void* hi, void* lo,
