@@ -15,70 +15,6 @@ __device__ __forceinline__ float4 prelu4(float4 v, float a) {
 __device__ __forceinline__ float dprelu(float z, float a) { return z > 0.f ? 1.f : a; }
 
 // ---------------------------------------------------------------------------------------
-// Encoder: w[m,k,n] = relu(sum_l U[n,l] * mix[m, k*S + l])        (src/conv_tasnet.py:119-120)
-// grid (frame tiles, M), block 256.  smem: U^T [L][N] + the tile's samples.
-// ---------------------------------------------------------------------------------------
-constexpr int ENC_TK = 16;
-__global__ void __launch_bounds__(256) encoder_fwd_kernel(const float* __restrict__ mix, const float* __restrict__ U,
-                                                          int T, int K, int N, int L, float* __restrict__ w) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float sm[];
-  float* Ut = sm;           // [L][N]
-  float* xs = sm + L * N;   // [ENC_TK*S + L]
-  const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENC_TK;
-  const int nk = min(ENC_TK, K - k0);
-  for (int i = threadIdx.x; i < N * L; i += blockDim.x) {
-    const int n = i / L, l = i - n * L;
-    Ut[l * N + n] = U[i];
-  }
-  const int nx = (nk - 1) * S + L;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = mix[(int64_t)m * T + (int64_t)k0 * S + i];
-  __syncthreads();
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    for (int k = 0; k < nk; ++k) {
-      float acc = 0.f;
-      for (int l = 0; l < L; ++l) acc = fmaf(Ut[l * N + n], xs[k * S + l], acc);
-      w[((int64_t)m * K + k0 + k) * N + n] = fmaxf(acc, 0.f);
-    }
-  }
-}
-
-// dU[n,l] += sum_{f in tile} (dwa+dwb)[f,n] * [w[f,n] > 0] * mix[m, k*S+l]   (thread per n, accumulators in registers)
-constexpr int ENCB_TK = 32;
-constexpr int ENC_MAXL = 32;
-__global__ void __launch_bounds__(256) encoder_bwd_kernel(const float* __restrict__ mix, const float* __restrict__ w,
-                                                          const float* __restrict__ dwa, const float* __restrict__ dwb,
-                                                          int T, int K, int N, int L, float* __restrict__ dU) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float sm[];
-  float* xs = sm;  // [ENCB_TK*S + L]
-  const int S = L / 2, m = blockIdx.y, k0 = blockIdx.x * ENCB_TK;
-  const int nk = min(ENCB_TK, K - k0);
-  const int nx = (nk - 1) * S + L;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = mix[(int64_t)m * T + (int64_t)k0 * S + i];
-  __syncthreads();
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float acc[ENC_MAXL];
-#pragma unroll
-    for (int l = 0; l < ENC_MAXL; ++l) acc[l] = 0.f;
-    for (int k = 0; k < nk; ++k) {
-      const int64_t idx = ((int64_t)m * K + k0 + k) * N + n;
-      float g = dwa[idx];
-      if (dwb != nullptr) g += dwb[idx];
-      if (!(w[idx] > 0.f)) g = 0.f;
-#pragma unroll
-      for (int l = 0; l < ENC_MAXL; ++l)
-        if (l < L) acc[l] = fmaf(g, xs[k * S + l], acc[l]);
-    }
-#pragma unroll
-    for (int l = 0; l < ENC_MAXL; ++l)
-      if (l < L) atomicAdd(dU + n * L + l, acc[l]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // cLN statistics: one warp per frame, two-pass like torch.var (src/conv_tasnet.py:332-333)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
@@ -153,8 +89,14 @@ __global__ void __launch_bounds__(256) prep_normfold_kernel(const float* __restr
 // a P-deep register window (instead of being re-read from L2 once per tap).
 // grid (classes * segments, M), block = H/4 threads rounded up to a warp (<= 256, loops over channel groups)
 // ---------------------------------------------------------------------------------------
-constexpr int DW_TJ = 16;  // outputs per block (per channel group)
-constexpr int DW_U = 4;    // outputs per inner group: DW_U independent loads in flight
+#ifndef CTN_DW_TJ
+#define CTN_DW_TJ 16
+#endif
+#ifndef CTN_DW_U
+#define CTN_DW_U 4
+#endif
+constexpr int DW_TJ = CTN_DW_TJ;  // outputs per block (per channel group)
+constexpr int DW_U = CTN_DW_U;    // outputs per inner group: DW_U independent loads in flight
 constexpr int MAXP = 8;
 
 __host__ __device__ inline int dw_classes(int K, int dil) { return dil < K ? dil : K; }
@@ -415,7 +357,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // norm backward, reduction pass: per-channel sums (dn*yhat, dn) leave the block as a [2][Ch] row of `part`
 // (folded by reduce_partials_kernel with P = 0); red[m] += (sum dn*gamma, sum dn*gamma*yhat)
 // ---------------------------------------------------------------------------------------
-constexpr int NR_TK = 16;
+#ifndef CTN_NR_TK
+#define CTN_NR_TK 16
+#endif
+constexpr int NR_TK = CTN_NR_TK;
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ dn, const float* __restrict__ z,
                                                               const float* __restrict__ alpha, NormStats st,
                                                               const float* __restrict__ gamma, int K, int Ch,
@@ -484,7 +429,10 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 }
 
 // apply pass, gLN: dz = r*(dn*gamma - m1 - yhat*m2) * prelu'(z); dalpha += sum da * z * [z<=0]
-constexpr int GA_TK = 8;
+#ifndef CTN_GA_TK
+#define CTN_GA_TK 8
+#endif
+constexpr int GA_TK = CTN_GA_TK;
 __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
                                                             const float* __restrict__ alpha, NormStats st,
                                                             const float* __restrict__ gamma, const double* __restrict__ redin,
@@ -595,184 +543,6 @@ __global__ void __launch_bounds__(256) cln_bwd_apply_kernel(float* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// Decoder forward: mask nonlinearity, * w, basis V, overlap-add with step S = L/2, zero pad to T.
-// grid (frame tiles, M); one warp per frame computes frames[k][c][l]; then the block writes its
-// span of output samples (each sample sums the <= ceil(L/S) frames that cover it, ascending k).
-// ---------------------------------------------------------------------------------------
-constexpr int DEC_TK = 16;
-constexpr int MAXC = 4;
-constexpr int DEC_MAXN = 16;  // per-lane basis channels (N <= 512)
-__global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restrict__ score, const float* __restrict__ w,
-                                                          const float* __restrict__ V, int K, int C, int N, int L,
-                                                          int T, int softmax, float* __restrict__ est) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float sm[];
-  const int S = L / 2;
-  const int halo = (L - 1) / S;  // frames before the tile that still reach into it
-  float* Vs = sm;                               // [L][N]
-  float* fr = Vs + L * N;                       // [(DEC_TK + halo)][C][L]
-  const int m = blockIdx.y, k0 = blockIdx.x * DEC_TK;
-  const int kb = max(0, k0 - halo), ke = min(K, k0 + DEC_TK);
-  for (int i = threadIdx.x; i < L * N; i += blockDim.x) Vs[i] = V[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int k = kb + wid; k < ke; k += nw) {  // one frame per warp: lanes own n = lane + 32 i
-    const int64_t f = (int64_t)m * K + k;
-    float sw[MAXC][DEC_MAXN];
-    const int ni = (N + 31) >> 5;  // per-lane channels actually present
-#pragma unroll
-    for (int i = 0; i < DEC_MAXN; ++i) {
-      if (i >= ni) {
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) sw[c][i] = 0.f;
-        continue;
-      }
-      const int n = lane + 32 * i;
-      float sc[MAXC];
-      const float wv = n < N ? w[f * N + n] : 0.f;
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) sc[c] = (c < C && n < N) ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
-      if (softmax) {
-        float mx = sc[0];
-#pragma unroll
-        for (int c = 1; c < MAXC; ++c) mx = fmaxf(mx, sc[c]);
-        float den = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) { sc[c] = (c < C && n < N) ? expf(sc[c] - mx) : 0.f; den += sc[c]; }
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) sw[c][i] = n < N ? sc[c] / den * wv : 0.f;
-      } else {
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) sw[c][i] = fmaxf(sc[c], 0.f) * wv;
-      }
-    }
-    float* out = fr + (k - kb) * C * L;
-    for (int c = 0; c < C; ++c) {
-      for (int l = 0; l < L; ++l) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < DEC_MAXN; ++i) {
-          if (i >= ni) break;
-          const int n = lane + 32 * i;
-          float swv = sw[0][i];
-#pragma unroll
-          for (int cc = 1; cc < MAXC; ++cc)
-            if (cc == c) swv = sw[cc][i];
-          if (n < N) acc = fmaf(swv, Vs[l * N + n], acc);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) out[c * L + l] = acc;
-      }
-    }
-  }
-  __syncthreads();
-  // output span of this tile: [k0*S, (k0+DEC_TK)*S), the last tile runs to T (tail + zero pad)
-  const int t0 = k0 * S;
-  const int t1 = (k0 + DEC_TK >= K) ? T : (k0 + DEC_TK) * S;
-  for (int c = 0; c < C; ++c) {
-    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-      float acc = 0.f;
-      const int khi = min(t / S, K - 1);
-      int klo = (t - L + S) / S;  // ceil((t-L+1)/S) for t-L+1 >= 0
-      if (t - L + 1 <= 0) klo = 0;
-      for (int k = max(klo, kb); k <= khi; ++k) {
-        const int l = t - k * S;
-        if (l >= 0 && l < L) acc += fr[((k - kb) * C + c) * L + l];
-      }
-      est[((int64_t)m * C + c) * T + t] = acc;
-    }
-  }
-}
-
-// Decoder backward: thread per basis channel n (its V column and dV accumulators live in registers), loop over the
-// tile's frames.
-constexpr int DECB_TK = 32;
-constexpr int DEC_MAXL = 32;
-__global__ void __launch_bounds__(256) decoder_bwd_kernel(const float* __restrict__ d_est, const float* __restrict__ score,
-                                                          const float* __restrict__ w, const float* __restrict__ V, int K,
-                                                          int C, int N, int L, int T, int softmax,
-                                                          float* __restrict__ d_score, float* __restrict__ d_w,
-                                                          float* __restrict__ dV) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float sm[];
-  const int S = L / 2;
-  float* df = sm;  // [DECB_TK][C][L]
-  const int m = blockIdx.y, k0 = blockIdx.x * DECB_TK;
-  const int nk = min(DECB_TK, K - k0);
-  for (int i = threadIdx.x; i < nk * C * L; i += blockDim.x) {
-    const int l = i % L, c = (i / L) % C, kk = i / (L * C);
-    df[i] = d_est[((int64_t)m * C + c) * T + (int64_t)(k0 + kk) * S + l];
-  }
-  __syncthreads();
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float vcol[DEC_MAXL], dvacc[DEC_MAXL];
-#pragma unroll
-    for (int l = 0; l < DEC_MAXL; ++l) {
-      vcol[l] = l < L ? V[l * N + n] : 0.f;
-      dvacc[l] = 0.f;
-    }
-    for (int kk = 0; kk < nk; ++kk) {
-      const int64_t f = (int64_t)m * K + k0 + kk;
-      const float wv = w[f * N + n];
-      float sc[MAXC], mk[MAXC], dsw[MAXC];
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) sc[c] = c < C ? score[f * (int64_t)(C * N) + c * N + n] : -INFINITY;
-      if (softmax) {
-        float mx = sc[0];
-#pragma unroll
-        for (int c = 1; c < MAXC; ++c) mx = fmaxf(mx, sc[c]);
-        float den = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) { mk[c] = c < C ? expf(sc[c] - mx) : 0.f; den += mk[c]; }
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) mk[c] /= den;
-      } else {
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) mk[c] = fmaxf(sc[c], 0.f);
-      }
-      float dwv = 0.f;
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        dsw[c] = 0.f;
-        if (c < C) {
-          const float* dfc = df + (kk * C + c) * L;
-          const float sw = mk[c] * wv;
-          float acc = 0.f;
-#pragma unroll
-          for (int l = 0; l < DEC_MAXL; ++l) {
-            if (l < L) {
-              const float d = dfc[l];
-              acc = fmaf(d, vcol[l], acc);
-              dvacc[l] = fmaf(d, sw, dvacc[l]);
-            }
-          }
-          dsw[c] = acc;
-          dwv = fmaf(acc, mk[c], dwv);
-        }
-      }
-      d_w[f * N + n] = dwv;
-      if (softmax) {
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) dot = fmaf(dsw[c] * wv, mk[c], dot);
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-          if (c < C) d_score[f * (int64_t)(C * N) + c * N + n] = mk[c] * (dsw[c] * wv - dot);
-      } else {
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-          if (c < C) d_score[f * (int64_t)(C * N) + c * N + n] = sc[c] > 0.f ? dsw[c] * wv : 0.f;
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < DEC_MAXL; ++l)
-      if (l < L) atomicAdd(dV + l * N + n, dvacc[l]);
-  }
-}
-
 // utils.overlap_and_add as a standalone op: out[o, t] = sum_k sig[o, k, t - k*step], ascending k
 __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ sig, int frames, int flen, int step,
                                                   int64_t out_len, float* __restrict__ out) {
@@ -794,38 +564,11 @@ static int block_for_channels(int Ch) {
   return t > 256 ? 256 : (t < 32 ? 32 : t);
 }
 
-static int ensure_smem(const void* fn, size_t bytes) {
-  if (bytes > 48 * 1024) {  // (set on every such launch: the attribute is per device and these launches are rare)
-    CTN_REQUIRE(bytes <= 227 * 1024, "kernel needs %zu bytes of shared memory (> 227 KB): N*L too large", bytes);
-    CTN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  }
-  return 0;
-}
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
 // host launchers (C linkage wrappers live in c_api.cu)
 // ---------------------------------------------------------------------------------------
-int run_encoder_fwd(const float* mix, const float* U, int M, int T, int N, int L, float* w, cudaStream_t s) {
-  CTN_REQUIRE(L >= 2 && T >= L, "encoder: need L >= 2 and T >= L (T=%d L=%d)", T, L);
-  const int S = L / 2, K = (T - L) / S + 1;
-  const size_t smem = (size_t)(L * N + ENC_TK * S + L) * sizeof(float);
-  CTN_TRY(ensure_smem((const void*)encoder_fwd_kernel, smem));
-  launch_kernel(encoder_fwd_kernel, dim3(cdiv(K, ENC_TK), M), 256, smem, s, mix, U, T, K, N, L, w);
-  return check_launch("encoder_fwd_kernel");
-}
-
-int run_encoder_bwd(const float* mix, const float* w, const float* dwa, const float* dwb, int M, int T, int N, int L,
-                    float* dU, cudaStream_t s) {
-  const int S = L / 2, K = (T - L) / S + 1;
-  CTN_REQUIRE(L <= ENC_MAXL, "encoder: L <= %d supported (got %d)", ENC_MAXL, L);
-  const size_t smem = (size_t)(ENCB_TK * S + L) * sizeof(float);
-  CTN_TRY(ensure_smem((const void*)encoder_bwd_kernel, smem));
-  launch_kernel(encoder_bwd_kernel, dim3(cdiv(K, ENCB_TK), M), 256, smem, s, mix, w, dwa, dwb, T, K, N, L, dU);
-  return check_launch("encoder_bwd_kernel");
-}
-
 int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s) {
   CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
   launch_kernel(row_stats_kernel, cdiv(F, 8), 256, 0, s, x, alpha, F, Ch, rowstat);
@@ -955,27 +698,6 @@ int run_fold_batch(const FoldBatch& fb, int n_entries, cudaStream_t s) {
   splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
   launch_kernel(reduce_partials_batch_kernel, dim3(cdiv(maxn, 256), splits, n_entries), 256, 0, s, fb);
   return check_launch("reduce_partials_batch_kernel");
-}
-
-int run_decoder_fwd(const float* score, const float* w, const float* V, int M, int K, int C, int N, int L, int T,
-                    int softmax, float* est, cudaStream_t s) {
-  CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
-  const int S = L / 2, halo = (L - 1) / S;
-  CTN_REQUIRE(N <= 32 * DEC_MAXN, "decoder: N <= %d supported (got %d)", 32 * DEC_MAXN, N);
-  const size_t smem = (size_t)(L * N + (DEC_TK + halo) * C * L) * sizeof(float);
-  CTN_TRY(ensure_smem((const void*)decoder_fwd_kernel, smem));
-  launch_kernel(decoder_fwd_kernel, dim3(cdiv(K, DEC_TK), M), 256, smem, s, score, w, V, K, C, N, L, T, softmax, est);
-  return check_launch("decoder_fwd_kernel");
-}
-
-int run_decoder_bwd(const float* d_est, const float* score, const float* w, const float* V, int M, int K, int C, int N,
-                    int L, int T, int softmax, float* d_score, float* d_w, float* dV, cudaStream_t s) {
-  CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
-  CTN_REQUIRE(L <= DEC_MAXL, "decoder: L <= %d supported (got %d)", DEC_MAXL, L);
-  const size_t smem = (size_t)(DECB_TK * C * L) * sizeof(float);
-  CTN_TRY(ensure_smem((const void*)decoder_bwd_kernel, smem));
-  launch_kernel(decoder_bwd_kernel, dim3(cdiv(K, DECB_TK), M), 256, smem, s, d_est, score, w, V, K, C, N, L, T, softmax, d_score, d_w, dV);
-  return check_launch("decoder_bwd_kernel");
 }
 
 int run_overlap_and_add(const float* sig, int64_t outer, int frames, int flen, int step, float* out, cudaStream_t s) {
