@@ -807,15 +807,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
       // ---- epilogue: atomically add the partial tile ----
       mbar_wait(tmem_full, 0);
       tc_fence_after();
+      // TMEM gives lane = output row o, registers = columns i: adding from there would scatter every warp instruction
+      // over 32 rows.  Each warp therefore stages its [32 rows x NI/2 columns] quadrant in shared memory (the operand
+      // stages are free: every MMA has completed) and adds it row-wise, 512 contiguous bytes per warp instruction.
       const int q = warp & 3, half = (warp - 4) >> 2;
-      const int o = o0 + q * 32 + lane;
       const int jb = half * (NI / 2), je = jb + NI / 2;
+      constexpr int PITCH = NI + 4;  // floats; 16-byte row alignment, conflict-free 16-byte stores down a column
+      const uint32_t srow = smem_base + (uint32_t)(((q * 32 + lane) * PITCH + jb) * 4);
       for (int j = jb; j < je; j += 8) {
         float acc[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
-        float* dst = a.dW + (int64_t)o * a.I + i0 + j;
-        red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
-        red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+        sts128(srow + (uint32_t)((j - jb) * 4), make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]),
+                                                           __float_as_uint(acc[2]), __float_as_uint(acc[3])));
+        sts128(srow + (uint32_t)((j - jb) * 4 + 16), make_uint4(__float_as_uint(acc[4]), __float_as_uint(acc[5]),
+                                                                __float_as_uint(acc[6]), __float_as_uint(acc[7])));
+      }
+      __syncwarp();
+      constexpr int LPR = NI / 8;    // lanes per row (float4 each) of the quadrant
+      constexpr int RPI = 32 / LPR;  // rows per warp instruction
+      const int rsub = lane / LPR, col = jb + (lane % LPR) * 4;
+#pragma unroll 4
+      for (int r = 0; r < 32; r += RPI) {
+        const int row = q * 32 + r + rsub;
+        const float4 v = lds128f(smem_base + (uint32_t)((row * PITCH + col) * 4));
+        red_add_v4(a.dW + (int64_t)(o0 + row) * a.I + i0 + col, v.x, v.y, v.z, v.w);
       }
     }
   }
