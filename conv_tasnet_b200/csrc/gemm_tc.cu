@@ -645,8 +645,13 @@ struct TcWgradArgs {
 };
 
 constexpr int WG_STAT_CACHE = 16;  // samples whose (mean, rstd) a CTA caches; more fall back to load_stats per row
+#ifndef CTN_WGT
+#define CTN_WGT 256
+#endif
+constexpr int WGT = CTN_WGT;               // threads of one converter group (two groups alternate k-blocks)
+constexpr int W_THREADS = 128 + 2 * WGT;   // 4 control warps + the converter / epilogue warps
 template <int NI>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
+__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
   pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();
     for (int s = 0; s < WSTAGES; ++s) {
-      mbar_init(full + s, CONV_THREADS / 2);  // one converter group per k-block
+      mbar_init(full + s, WGT);  // one converter group per k-block
       mbar_init(empty + s, 1);
     }
     mbar_init(tmem_full, 1);
@@ -709,14 +714,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
       }
     } else if (warp >= 4) {
       const int t = threadIdx.x - 128;
-      const int grp = t >> 7, tg = t & 127;  // two groups of 4 warps alternate k-blocks (see tc_gemm_kernel)
+      const int grp = t / WGT, tg = t % WGT;  // two groups of WGT threads alternate k-blocks (see tc_gemm_kernel)
       const bool norm = a.gamma != nullptr, hasp = a.alpha != nullptr;
       const float alpha = hasp ? __ldg(a.alpha) : 1.f;
-      // G tile: 32 rows x 16 chunks (8 floats each): 4 chunks per thread (rows tg/16 + 8*it)
+      // G tile: 32 rows x 16 chunks (8 floats each): GIT chunks per thread (rows tg/16 + GR*it)
+      constexpr int GR = WGT / 16, GIT = WK / GR;
       const int gc = tg & 15, gr = tg >> 4;
       // Act tile: 32 rows x NI/8 chunks
       constexpr int XC = NI / 8;        // chunks per row
-      constexpr int XR = 128 / XC;      // rows covered per pass
+      constexpr int XR = WGT / XC;      // rows covered per pass
       constexpr int XIT = WK / XR;
       const int xc = tg % XC, xr = tg / XC;
       float gam[8], bet[8];
@@ -735,15 +741,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
           load_stats(a.st, m_lo + t, 0, mu, r);
           s_wst[t] = make_float2(mu, r);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(2 * WGT) : "memory");
       }
       for (int kb = grp; kb < nkb; kb += 2) {
         const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
         const int64_t fk = fb + (int64_t)kb * WK;
-        float4 gv[4][2], xv[XIT][2];
+        float4 gv[GIT][2], xv[XIT][2];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int64_t f = fk + gr + it * 8;
+        for (int it = 0; it < GIT; ++it) {
+          const int64_t f = fk + gr + it * GR;
           const bool ok = f < fe;
           const float4* src = reinterpret_cast<const float4*>(a.G + f * a.O + o0 + gc * 8);
           gv[it][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -760,8 +766,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
         mbar_wait(empty + s, ph ^ 1);
         const uint32_t st = smem_base + s * STAGE;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int k = gr + it * 8;
+        for (int it = 0; it < GIT; ++it) {
+          const int k = gr + it * GR;
           const float x[8] = {gv[it][0].x, gv[it][0].y, gv[it][0].z, gv[it][0].w,
                               gv[it][1].x, gv[it][1].y, gv[it][1].z, gv[it][1].w};
           uint4 hi, lo;
@@ -810,8 +816,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
       // TMEM gives lane = output row o, registers = columns i: adding from there would scatter every warp instruction
       // over 32 rows.  Each warp therefore stages its [32 rows x NI/2 columns] quadrant in shared memory (the operand
       // stages are free: every MMA has completed) and adds it row-wise, 512 contiguous bytes per warp instruction.
-      const int q = warp & 3, half = (warp - 4) >> 2;
-      const int jb = half * (NI / 2), je = jb + NI / 2;
+      constexpr int CSPLIT = (2 * WGT / 32) / 4;  // warps sharing a TMEM lane quarter: each takes NI / CSPLIT columns
+      constexpr int QC = NI / CSPLIT;
+      const int q = warp & 3, part = (warp - 4) >> 2;
+      const int jb = part * QC, je = jb + QC;
       constexpr int PITCH = NI + 4;  // floats; 16-byte row alignment, conflict-free 16-byte stores down a column
       const uint32_t srow = smem_base + (uint32_t)(((q * 32 + lane) * PITCH + jb) * 4);
       for (int j = jb; j < je; j += 8) {
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) 
                                                                 __float_as_uint(acc[6]), __float_as_uint(acc[7])));
       }
       __syncwarp();
-      constexpr int LPR = NI / 8;    // lanes per row (float4 each) of the quadrant
+      constexpr int LPR = QC / 4;    // lanes per row (float4 each) of the quadrant
       constexpr int RPI = 32 / LPR;  // rows per warp instruction
       const int rsub = lane / LPR, col = jb + (lane % LPR) * 4;
 #pragma unroll 4
@@ -1068,10 +1076,10 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
   }
   if (ni == 256) {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128 + 8 * WG_STAT_CACHE;
-    launch_kernel(tc_wgrad_kernel<256>, grid, TC_THREADS, smem, s, a);
+    launch_kernel(tc_wgrad_kernel<256>, grid, W_THREADS, smem, s, a);
   } else {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128 + 8 * WG_STAT_CACHE;
-    launch_kernel(tc_wgrad_kernel<128>, grid, TC_THREADS, smem, s, a);
+    launch_kernel(tc_wgrad_kernel<128>, grid, W_THREADS, smem, s, a);
   }
   return check_launch(w.gamma != nullptr ? "tc_wgrad_kernel (norm prologue)" : "tc_wgrad_kernel (plain)");
 }
