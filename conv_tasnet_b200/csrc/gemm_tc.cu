@@ -231,8 +231,19 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-constexpr int TC_THREADS = 384;       // 4 control warps + 8 converter/epilogue warps
-constexpr int CONV_THREADS = 256;
+#ifndef CTN_CONV_THREADS
+#define CTN_CONV_THREADS 256
+#endif
+constexpr int CONV_THREADS = CTN_CONV_THREADS;  // converter / epilogue threads (8 or 16 warps)
+constexpr int TC_THREADS = 128 + CONV_THREADS;  // + 4 control warps
+#ifndef CTN_CONV_THREADS_BF16
+#define CTN_CONV_THREADS_BF16 512
+#endif
+constexpr int CONV_THREADS_BF16 = CTN_CONV_THREADS_BF16;
+#ifndef CTN_TC_MAX_GROUPS
+#define CTN_TC_MAX_GROUPS (CTN_CONV_THREADS > 256 ? 2 : 4)
+#endif
+constexpr int TC_MAX_GROUPS = CTN_TC_MAX_GROUPS;  // main TF32 accumulators (register budget of the epilogue)
 constexpr int BM = 128;               // MMA M (output channels)
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
 constexpr int STAGES = 2;             // operand stages (hi/lo planes of W and A)
@@ -269,10 +280,13 @@ struct TcGemmArgs {
 // 2 = TMEM allocator, 4..11 = converters (smem raw fp32 -> prologue -> hi/lo split -> swizzled operand planes; no global
 // loads, so nothing is in flight when they fence) and afterwards the epilogue.
 template <bool TF32, bool FOLD, bool RES, bool STATS, bool NRED = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TF32 ? 128 + CONV_THREADS : 128 + CONV_THREADS_BF16, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_a, TcGemmArgs a) {
   pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
+  // converter / epilogue threads: the bf16 (gradient) flavour runs 16 warps (measured: its longer K loop gains from the
+  // extra converters and its one-accumulator epilogue fits the register budget), the TF32 flavour 8 (150 registers)
+  constexpr int CT = TF32 ? CONV_THREADS : CONV_THREADS_BF16;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int NF = a.NF, NST = a.stages, RST = a.raw_stages;
   const int a_plane = NF * 128;
@@ -299,12 +313,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full + s, 1 + CONV_THREADS);  // weight TMA producer + every converter thread
+      mbar_init(full + s, 1 + CT);  // weight TMA producer + every converter thread
       mbar_init(empty + s, 1);
     }
     for (int r = 0; r < RST; ++r) {
       mbar_init(raw_full + r, 1);
-      mbar_init(raw_empty + r, CONV_THREADS);
+      mbar_init(raw_empty + r, CT);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -402,16 +416,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         // same element size in and out: the swizzled position of a 16-byte chunk is identical in the raw tile and
         // in the operand planes, so the conversion is position-agnostic
         // batches of 5 chunks per thread: all shared loads first (ILP), then convert + store
-        for (int q0 = t; q0 < nchunks; q0 += 5 * CONV_THREADS) {
+        for (int q0 = t; q0 < nchunks; q0 += 5 * CT) {
           float4 x[5];
 #pragma unroll
           for (int u = 0; u < 5; ++u) {
-            const int q = q0 + u * CONV_THREADS;
+            const int q = q0 + u * CT;
             if (q < nchunks) x[u] = lds128f(raw + q * 16);
           }
 #pragma unroll
           for (int u = 0; u < 5; ++u) {
-            const int q = q0 + u * CONV_THREADS;
+            const int q = q0 + u * CT;
             if (q < nchunks) {
               float4 y = x[u];
               if (pro) { y.x = prelu(y.x, alpha_in); y.y = prelu(y.y, alpha_in); y.z = prelu(y.z, alpha_in); y.w = prelu(y.w, alpha_in); }
@@ -424,11 +438,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         }
       } else {
         // bf16 chunk oc of row `row` = K elements [8 oc, 8 oc + 8) = raw box (oc >> 2), raw chunks 2 (oc & 3), +1
-        for (int q0 = t; q0 < nchunks; q0 += 5 * CONV_THREADS) {
+        for (int q0 = t; q0 < nchunks; q0 += 5 * CT) {
           float4 x0[5], x1[5];
 #pragma unroll
           for (int u = 0; u < 5; ++u) {
-            const int q = q0 + u * CONV_THREADS;
+            const int q = q0 + u * CT;
             if (q < nchunks) {
               const int row = q >> 3, oc = q & 7, sw = row & 7;
               const uint32_t rb = raw + (oc >> 2) * a_plane + row * 128;
@@ -439,7 +453,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           }
 #pragma unroll
           for (int u = 0; u < 5; ++u) {
-            const int q = q0 + u * CONV_THREADS;
+            const int q = q0 + u * CT;
             if (q < nchunks) {
               const int row = q >> 3, oc = q & 7, sw = row & 7;
               float x[8] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w, x1[u].x, x1[u].y, x1[u].z, x1[u].w};
@@ -473,17 +487,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       s_m[t] = m;
       s_col[t] = make_float2(r, mu * r);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // column metadata written by the converter threads
+    asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");  // column metadata written by the converter threads
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (t == 0) TR(3);
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, part = (warp - 4) >> 2;  // TMEM lane quarter; column range among the warps sharing it
+    constexpr int CPARTS = CT / 128;
     const int o = o0 + q * 32 + lane;
     const int O = a.O;
     const float c1 = FOLD ? __ldg(a.c1 + o) : 0.f, c2 = FOLD ? __ldg(a.c2 + o) : 0.f;
     const float alpha_out = (STATS && a.alpha_out) ? __ldg(a.alpha_out) : 1.f;
-    const int jb = half * (NF / 2);
-    const int je = min(jb + NF / 2, nvalid);
+    const int nch = NF >> 3;  // 8-column chunks of the tile
+    const int jb = 8 * ((part * nch) / CPARTS);
+    const int je = min(8 * (((part + 1) * nch) / CPARTS), nvalid);
     float* dptr = a.D + f0 * O + o;
     const float* rptr = RES ? a.res + f0 * O + o : nullptr;
     const uint32_t col_s = smem_u32(s_col);
@@ -495,7 +511,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const bool nr_prelu = NRED && a.nred_alpha != nullptr;
     const float nr_gamma = NRED ? __ldg(a.nred_gamma + o) : 0.f;
     float nr_dg = 0.f, nr_db = 0.f;
-    constexpr int NACC = TF32 ? 5 : 1;  // TMEM tiles summed per output (NG main + 1 correction, NG <= 4)
+    constexpr int NACC = TF32 ? TC_MAX_GROUPS + 1 : 1;  // TMEM tiles summed per output (NG main + 1 correction)
     uint32_t rawA[NACC][8], rawB[NACC][8];
     auto issue = [&](uint32_t (&dst)[NACC][8], int j) {
 #pragma unroll
@@ -590,18 +606,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         }
       }
     };
-    // software pipeline: the TMEM loads of the next 8 columns are in flight while this chunk is processed
-    if (jb < je) issue(rawA, jb);
-    if (t == 0) TR(6);
-    for (int j = jb; j < je; j += 16) {
-      tmem_ld_wait();
-      if (t == 0 && j == jb) TR(7);
-      if (j + 8 < je) issue(rawB, j + 8);
-      process(rawA, j);
-      if (j + 8 < je) {
+    if (CT <= 256 || TC_MAX_GROUPS <= 2 || !TF32) {
+      // software pipeline: the TMEM loads of the next 8 columns are in flight while this chunk is processed
+      if (jb < je) issue(rawA, jb);
+      if (t == 0) TR(6);
+      for (int j = jb; j < je; j += 16) {
         tmem_ld_wait();
-        if (j + 16 < je) issue(rawA, j + 16);
-        process(rawB, j + 8);
+        if (t == 0 && j == jb) TR(7);
+        if (j + 8 < je) issue(rawB, j + 8);
+        process(rawA, j);
+        if (j + 8 < je) {
+          tmem_ld_wait();
+          if (j + 16 < je) issue(rawA, j + 16);
+          process(rawB, j + 8);
+        }
+      }
+    } else {  // 16 epilogue warps: four per TMEM lane quarter hide the load latency between them (and registers are scarce)
+      for (int j = jb; j < je; j += 8) {
+        issue(rawA, j);
+        tmem_ld_wait();
+        process(rawA, j);
       }
     }
     if ((STATS || NRED) && cur_m >= 0) {
@@ -648,8 +672,12 @@ constexpr int WG_STAT_CACHE = 16;  // samples whose (mean, rstd) a CTA caches; m
 #ifndef CTN_WGT
 #define CTN_WGT 256
 #endif
-constexpr int WGT = CTN_WGT;               // threads of one converter group (two groups alternate k-blocks)
-constexpr int W_THREADS = 128 + 2 * WGT;   // 4 control warps + the converter / epilogue warps
+#ifndef CTN_WNG
+#define CTN_WNG 2
+#endif
+constexpr int WGT = CTN_WGT;               // threads of one converter group
+constexpr int WNG = CTN_WNG;               // converter groups, taking k-blocks round robin
+constexpr int W_THREADS = 128 + WNG * WGT; // 4 control warps + the converter / epilogue warps
 template <int NI>
 __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
   pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
@@ -741,9 +769,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
           load_stats(a.st, m_lo + t, 0, mu, r);
           s_wst[t] = make_float2(mu, r);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(2 * WGT) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(WNG * WGT) : "memory");
       }
-      for (int kb = grp; kb < nkb; kb += 2) {
+      for (int kb = grp; kb < nkb; kb += WNG) {
         const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
         const int64_t fk = fb + (int64_t)kb * WK;
         float4 gv[GIT][2], xv[XIT][2];
@@ -816,9 +844,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
       // TMEM gives lane = output row o, registers = columns i: adding from there would scatter every warp instruction
       // over 32 rows.  Each warp therefore stages its [32 rows x NI/2 columns] quadrant in shared memory (the operand
       // stages are free: every MMA has completed) and adds it row-wise, 512 contiguous bytes per warp instruction.
-      constexpr int CSPLIT = (2 * WGT / 32) / 4;  // warps sharing a TMEM lane quarter: each takes NI / CSPLIT columns
+      constexpr int EW = (WNG * WGT / 32) >= 16 ? 16 : 8;  // epilogue warps (the first EW converter warps)
+      constexpr int CSPLIT = EW / 4;  // warps sharing a TMEM lane quarter: each takes NI / CSPLIT columns
       constexpr int QC = NI / CSPLIT;
       const int q = warp & 3, part = (warp - 4) >> 2;
+      if (warp - 4 < EW) {
       const int jb = part * QC, je = jb + QC;
       constexpr int PITCH = NI + 4;  // floats; 16-byte row alignment, conflict-free 16-byte stores down a column
       const uint32_t srow = smem_base + (uint32_t)(((q * 32 + lane) * PITCH + jb) * 4);
@@ -839,6 +869,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
         const int row = q * 32 + r + rsub;
         const float4 v = lds128f(smem_base + (uint32_t)((row * PITCH + col) * 4));
         red_add_v4(a.dW + (int64_t)(o0 + row) * a.I + i0 + col, v.x, v.y, v.z, v.w);
+      }
       }
     }
   }
@@ -1005,7 +1036,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   a.A = g.A; a.D = g.D; a.F = g.F; a.O = g.O; a.Kd = g.Kd; a.K = g.K;
   a.NF = pick_nf(g.F, g.O / BM, tf32);
   a.groups = 512 / a.NF - 1;
-  if (a.groups > 4) a.groups = 4;
+  if (a.groups > TC_MAX_GROUPS) a.groups = TC_MAX_GROUPS;
   a.alpha_in = g.alpha_in; a.c1 = g.c1; a.c2 = g.c2; a.st = g.st; a.res = g.res;
   a.stat_out = g.stat_out; a.alpha_out = g.alpha_out;
   a.nred_z = g.nred_z; a.nred_alpha = g.nred_alpha; a.nred_gamma = g.nred_gamma;
@@ -1018,6 +1049,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
   CTN_REQUIRE(a.raw_stages >= 2 && smem <= 227 * 1024, "tc_gemm: shared memory %zu too large", smem);
   dim3 grid(cdiv(g.F, a.NF), g.O / BM);
   const bool fold = g.c1 != nullptr, res = g.res != nullptr, stats = g.stat_out != nullptr;
+  const int threads = 128 + (tf32 ? CONV_THREADS : CONV_THREADS_BF16);
 #define CTN_TC_LAUNCH(...)                                                                                       \
   do {                                                                                                           \
     static unsigned long long attr_mask = 0;  /* the attribute is per device */                                  \
@@ -1028,7 +1060,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t s) {
                                     227 * 1024));                                                                \
       attr_mask |= 1ull << (dev__ & 63);                                                                         \
     }                                                                                                            \
-    launch_kernel(tc_gemm_kernel<__VA_ARGS__>, grid, TC_THREADS, smem, s, mh, ml, ma, a);                                   \
+    launch_kernel(tc_gemm_kernel<__VA_ARGS__>, grid, threads, smem, s, mh, ml, ma, a);                                   \
   } while (0)
   if (tf32) {  // forward 1x1 convs
     if (!fold && !res && !stats) CTN_TC_LAUNCH(true, false, false, false);
