@@ -6,7 +6,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libctn_b200.so")
+# CTN_B200_LIB points at an alternative build of the library (A/B of compile-time tuning constants); default in-tree
+_LIB_PATH = os.environ.get("CTN_B200_LIB") or os.path.join(_HERE, "libctn_b200.so")
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

@@ -243,6 +243,10 @@ constexpr int CONV_THREADS_BF16 = CTN_CONV_THREADS_BF16;
 #ifndef CTN_TC_MAX_GROUPS
 #define CTN_TC_MAX_GROUPS (CTN_CONV_THREADS > 256 ? 2 : 4)
 #endif
+#ifndef CTN_TF32_NF_MAX
+#define CTN_TF32_NF_MAX 160
+#endif
+constexpr int TF32_NF_MAX = CTN_TF32_NF_MAX;  // frames per forward tile: (groups + 1) * NF <= 512 TMEM columns
 constexpr int TC_MAX_GROUPS = CTN_TC_MAX_GROUPS;  // main TF32 accumulators (register budget of the epilogue)
 constexpr int BM = 128;               // MMA M (output channels)
 constexpr int BK = 64;                // bf16 elements per 128-byte swizzle row
@@ -991,7 +995,7 @@ static int pick_nf(int64_t F, int o_tiles, bool tf32) {
   // for >= 2 main accumulators + 1 correction accumulator in the 512 TMEM columns
   int best = 128;
   double best_cost = 1e30;
-  for (int nf = 64; nf <= (tf32 ? 160 : 256); nf += 16) {
+  for (int nf = 64; nf <= (tf32 ? TF32_NF_MAX : 256); nf += 16) {
     if (tc_gemm_raw_stages(nf, tf32) < 2) continue;  // operand stages + raw ring must fit in 227 KB
     const int64_t tiles = (F + nf - 1) / nf * o_tiles;
     const int64_t waves = (tiles + 147) / 148;

@@ -68,23 +68,44 @@ __global__ void step_inc_kernel(int64_t* step) {
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                                   float wd, const int64_t* __restrict__ step) {
+                                                   float wd, const int64_t* __restrict__ step, int vec) {
   pdl_launch_dependents();
   pdl_wait();
-  const double t = (double)step[0];
-  const float bias1 = (float)(1.0 - pow((double)b1, t));
-  const float bias2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  __shared__ float s_bias[2];
+  if (threadIdx.x == 0) {  // the fp64 pow()s once per block, not once per thread
+    const double t = (double)step[0];
+    s_bias[0] = (float)(1.0 - pow((double)b1, t));
+    s_bias[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float bias1 = s_bias[0], bias2_sqrt = s_bias[1];
   const float step_size = lr / bias1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i];
-    const float pi = p[i];
+  auto update = [&](float gi, float pi, float& mi, float& vi) {
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
+    mi = mi + (gi - mi) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * b2 + (1.f - b2) * gi * gi;
     const float denom = sqrtf(vi) / bias2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);
+    return pi - step_size * (mi / denom);
+  };
+  const int64_t n4 = vec ? n / 4 : 0;  // 16-byte aligned buffers: four parameters per thread and access
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    p4.x = update(g4.x, p4.x, m4.x, v4.x);
+    p4.y = update(g4.y, p4.y, m4.y, v4.y);
+    p4.z = update(g4.z, p4.z, m4.z, v4.z);
+    p4.w = update(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      float mi = m[i], vi = v[i];
+      p[i] = update(g[i], p[i], mi, vi);
+      m[i] = mi;
+      v[i] = vi;
+    }
   }
 }
 
@@ -106,7 +127,9 @@ int run_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float wd, int64_t* step_dev, cudaStream_t s) {
   launch_kernel(step_inc_kernel, 1, 1, 0, s, step_dev);
   CTN_TRY(check_launch("step_inc_kernel"));
-  launch_kernel(adam_kernel, 1184, 256, 0, s, p, g, m, v, n, lr, b1, b2, eps, wd, step_dev);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  launch_kernel(adam_kernel, 1184, 256, 0, s, p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, vec);
   return check_launch("adam_kernel");
 }
 

@@ -9,7 +9,7 @@ namespace {
 constexpr int PIT_MAXC = 4;
 constexpr int PIT_NMOM = 4 * PIT_MAXC + PIT_MAXC * PIT_MAXC + PIT_MAXC;  // Se, See, Ss_all, Ss, Sss, Ses
 constexpr int PIT_THREADS = 256;
-constexpr int PIT_PER_THREAD = 4;
+constexpr int PIT_PER_THREAD = 2;
 
 // moment slots for sample b (doubles):
 //   [0,C)        Se[i]    masked sum of est
@@ -43,22 +43,26 @@ __device__ void unrank_perm(int idx, int C, int* perm) {
   }
 }
 
+// templated on the number of speakers: every moment index is a compile-time constant (a run-time C put the 14..36
+// fp64 accumulators in local memory), and the block reduces all moments with two barriers instead of two per moment
+template <int C>
 __global__ void __launch_bounds__(PIT_THREADS) pit_moments_kernel(const float* __restrict__ src, float* __restrict__ est,
-                                                                  const int64_t* __restrict__ lengths, int B, int C,
+                                                                  const int64_t* __restrict__ lengths, int B, int,
                                                                   int T, PitWs ws, float* __restrict__ loss,
                                                                   float* __restrict__ max_snr, int64_t* __restrict__ idx_out,
                                                                   float* __restrict__ coef) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ double scratch[32];
+  constexpr int NM = 5 * C + C * C;
+  __shared__ double scratch[NM][PIT_THREADS / 32];
   __shared__ bool is_last;
   const int b = blockIdx.y;
   int64_t len = lengths[b];
   len = len < 0 ? 0 : (len > T ? T : len);
   const int64_t t0 = (int64_t)blockIdx.x * PIT_THREADS * PIT_PER_THREAD;
-  double mom[PIT_NMOM];
+  double mom[NM];
 #pragma unroll
-  for (int i = 0; i < PIT_NMOM; ++i) mom[i] = 0.0;
+  for (int i = 0; i < NM; ++i) mom[i] = 0.0;
   for (int it = 0; it < PIT_PER_THREAD; ++it) {
     const int64_t t = t0 + (int64_t)it * PIT_THREADS + threadIdx.x;
     if (t >= T) break;
@@ -95,11 +99,21 @@ __global__ void __launch_bounds__(PIT_THREADS) pit_moments_kernel(const float* _
       }
     }
   }
-  const int nm = 5 * C + C * C;
-  for (int i = 0; i < nm; ++i) {
-    double v[1] = {mom[i]};
-    block_sum<1>(v, scratch);
-    if (threadIdx.x == 0) atomicAdd(ws.mom + (int64_t)b * PIT_NMOM + i, v[0]);
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+      const double v = warp_sum(mom[i]);
+      if (lane == 0) scratch[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NM) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < PIT_THREADS / 32; ++w) v += scratch[threadIdx.x][w];
+      atomicAdd(ws.mom + (int64_t)b * PIT_NMOM + threadIdx.x, v);
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) {
     __threadfence();
@@ -233,7 +247,9 @@ int run_pit_forward(const float* source, float* est, const int64_t* lengths, int
   ws.ticket = reinterpret_cast<unsigned int*>(ws.mom + (int64_t)B * PIT_NMOM);
   ws.done = ws.ticket + B;
   const int chunks = cdiv(T, PIT_THREADS * PIT_PER_THREAD);
-  launch_kernel(pit_moments_kernel, dim3(chunks, B), PIT_THREADS, 0, s, source, est, lengths, B, C, T, ws, loss, max_snr, idx, coef);
+  auto kern = C == 1 ? pit_moments_kernel<1> : C == 2 ? pit_moments_kernel<2> : C == 3 ? pit_moments_kernel<3>
+                                                                                       : pit_moments_kernel<4>;
+  launch_kernel(kern, dim3(chunks, B), PIT_THREADS, 0, s, source, est, lengths, B, C, T, ws, loss, max_snr, idx, coef);
   CTN_TRY(check_launch("pit_moments_kernel"));
   if (reorder != nullptr) {
     int gx = cdiv(T, 256 * 8);
