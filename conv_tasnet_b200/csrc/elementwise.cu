@@ -95,15 +95,26 @@ __global__ void __launch_bounds__(256) prep_normfold_kernel(const float* __restr
 #ifndef CTN_DW_U
 #define CTN_DW_U 4
 #endif
-constexpr int DW_TJ = CTN_DW_TJ;  // outputs per block (per channel group)
+constexpr int DW_TJ = CTN_DW_TJ;  // backward: outputs per block (per channel group); one partial row per block
 constexpr int DW_U = CTN_DW_U;    // outputs per inner group: DW_U independent loads in flight
+#ifndef CTN_DWF_TJ
+#define CTN_DWF_TJ 16
+#endif
+#ifndef CTN_DWF_U
+#define CTN_DWF_U 4
+#endif
+constexpr int DWF_TJ = CTN_DWF_TJ;  // forward (no partial rows: its tile can differ from the backward's); measured
+                                    // (M = 3 x 4 s): eager in-place timing favours (32, 8) (16.4 vs 18.1 us) but the
+                                    // graph-replayed step is fastest with (16, 4): 6.29 vs 6.36 ms (register footprint
+                                    // under programmatic dependent launch); (8, 8) 25 us, (64, 8) 21 us
+constexpr int DWF_U = CTN_DWF_U;
 constexpr int MAXP = 8;
 
 __host__ __device__ inline int dw_classes(int K, int dil) { return dil < K ? dil : K; }
-__host__ __device__ inline int dw_blocks(int K, int dil) {
+__host__ __device__ inline int dw_blocks(int K, int dil, int tj = DW_TJ) {
   const int ncls = dw_classes(K, dil);
   const int per_class = (K + ncls - 1) / ncls;  // frames in the largest class
-  return ncls * ((per_class + DW_TJ - 1) / DW_TJ);
+  return ncls * ((per_class + tj - 1) / tj);
 }
 
 template <int PT>
@@ -119,9 +130,9 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
   __shared__ float2 s_st;
   const int m = blockIdx.y;
   const int ncls = dw_classes(K, dil);
-  const int r = blockIdx.x % ncls, j0 = (blockIdx.x / ncls) * DW_TJ;
+  const int r = blockIdx.x % ncls, j0 = (blockIdx.x / ncls) * DWF_TJ;
   const int nclass = (K - r + dil - 1) / dil;            // frames of this residue class
-  const int nj = max(0, min(DW_TJ, nclass - j0));        // outputs of this block
+  const int nj = max(0, min(DWF_TJ, nclass - j0));        // outputs of this block
   if (st1.row == nullptr) {
     if (threadIdx.x == 0) {
       float mu, rr;
@@ -165,13 +176,13 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
       else w[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float s = 0.f, s2 = 0.f;
-    for (int jj = 0; jj < nj; jj += DW_U) {
-      // the DW_U rows that enter the window after each of the next DW_U outputs: independent loads, issued together
-      float4 nraw[DW_U]; float2 nst[DW_U]; bool nok[DW_U];
+    for (int jj = 0; jj < nj; jj += DWF_U) {
+      // the DWF_U rows that enter the window after each of the next DWF_U outputs: independent loads, issued together
+      float4 nraw[DWF_U]; float2 nst[DWF_U]; bool nok[DWF_U];
 #pragma unroll
-      for (int u = 0; u < DW_U; ++u) fetch(j0 + jj + u + PP - cshift, nraw[u], nst[u], nok[u]);
+      for (int u = 0; u < DWF_U; ++u) fetch(j0 + jj + u + PP - cshift, nraw[u], nst[u], nok[u]);
 #pragma unroll
-      for (int u = 0; u < DW_U; ++u) {
+      for (int u = 0; u < DWF_U; ++u) {
         if (jj + u < nj) {
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -433,6 +444,10 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 #define CTN_GA_TK 8
 #endif
 constexpr int GA_TK = CTN_GA_TK;
+#ifndef CTN_GA_U
+#define CTN_GA_U 4
+#endif
+constexpr int GA_U = CTN_GA_U;
 __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
                                                             const float* __restrict__ alpha, NormStats st,
                                                             const float* __restrict__ gamma, const double* __restrict__ redin,
@@ -458,17 +473,17 @@ __global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ 
   for (int c = threadIdx.x * 4; c < Ch; c += blockDim.x * 4) {
     const float4 g = ld4(gamma + c);
     float s = 0.f;
-    for (int kk = 0; kk < nk; kk += 4) {
-      float4 zv[4], dv[4];
+    for (int kk = 0; kk < nk; kk += GA_U) {  // GA_U frames (2 x GA_U independent 16-byte loads) in flight per thread
+      float4 zv[GA_U], dv[GA_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GA_U; ++u) {
         const bool vk = kk + u < nk;
         const int64_t f = base + k0 + kk + u;
         zv[u] = vk ? ld4(z + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         dv[u] = vk ? ld4(dn + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GA_U; ++u) {
         if (kk + u >= nk) break;
         const int64_t f = base + k0 + kk + u;
         const float4 zz = zv[u], d = dv[u];
@@ -588,7 +603,7 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
   CTN_REQUIRE(P >= 1 && P <= MAXP, "dwconv: kernel size P must be in [1,%d] (got %d)", MAXP, P);
   CTN_REQUIRE(causal || (P % 2 == 1), "dwconv: non-causal needs odd P (reference output length changes otherwise)");
   const int cshift = causal ? P - 1 : (P - 1) / 2;
-  const dim3 grid(dw_blocks(K, dil), M);
+  const dim3 grid(dw_blocks(K, dil, DWF_TJ), M);
   if (P == 3)
     launch_kernel(dwconv_fwd_kernel<3>, grid, block_for_channels(H), 0, s, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, z2, stat_out, alpha2);
   else
