@@ -66,7 +66,11 @@ static inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  // eager launches gain ~10 % from the overlap; inside a captured graph the programmatic edges measured 0.5 % slower
+  // than plain kernel-to-kernel edges (6.285 vs 6.25 ms per step), so captures record ordinary launches
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors are picked up by check_launch()
   timing_note_stream(stream);
 }
