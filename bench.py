@@ -329,12 +329,14 @@ def main():
     flops = 2.0 * F * PAPER["B"] * PAPER["H"]
     ach = flops / t_k / 1e12
     roofline = {"kernel": "tc_wgrad_kernel<256>: dW[512,256] = dz1[F,512]^T x[F,256] (tcgen05, bf16x3 split, MN-major "
-                "operands, split-K + red.v4), 22.9 % of the step", "bound": "tensor", "achieved": ach,
+                "operands, split-K + coalesced red.v4), the largest single kernel of the step (2 per TemporalBlock + 2)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                 "traffic": 30054912, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per "
                 "launch (profiles/r1_final_wgrad_full_raw.csv); algorithmic input 29.5 MB",
                 "peak_source": pk_src + ", bf16 burst (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the "
-                "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops}
+                "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops,
+                "launches_per_step": 2 * PAPER["R"] * PAPER["X"] + 2,
+                "share_of_step": (2 * PAPER["R"] * PAPER["X"] + 2) * t_k / (secs / args.steps)}
 
     # whole-step algorithmic rates (SURVEY §8d per-frame figures x frames)
     frames = world * F
