@@ -314,16 +314,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   constexpr int KB = TF32 ? 32 : 64;  // elements per 128-byte swizzle row = K extent of one stage
   const int nkb = a.Kd / KB;
 
-  if (warp == 1 && lane == 0) {
-    if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
+  // Set-up, spread over the control warps so that the first TMA loads leave before the block-wide barrier: each producer
+  // thread initialises the barriers its own loads signal and issues its first ring of loads at once (after
+  // griddepcontrol.wait: both operands may have been written by the kernel right before this one).
+  const int pre_w = nkb < NST ? nkb : NST, pre_r = nkb < RST ? nkb : RST;
+  if (warp == 0 && lane == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(full + s, 1 + CT);  // weight TMA producer + every converter thread
       mbar_init(empty + s, 1);
     }
+    fence_barrier_init();
+    pdl_wait();  // (the planes may come from the kernel right before this one: BatchNorm fold, stand-alone calls)
+    for (int kb = 0; kb < pre_w; ++kb) {
+      uint8_t* st = smem + kb * stage_bytes;
+      mbar_expect_tx(full + kb, 2 * W_PLANE_BYTES);
+      tma_load_2d(st, &map_hi, full + kb, kb * KB, o0);
+      tma_load_2d(st + W_PLANE_BYTES, &map_lo, full + kb, kb * KB, o0);
+    }
+  } else if (warp == 3 && lane == 0) {
     for (int r = 0; r < RST; ++r) {
       mbar_init(raw_full + r, 1);
       mbar_init(raw_empty + r, CT);
     }
+    fence_barrier_init();
+    pdl_wait();
+    for (int kb = 0; kb < pre_r; ++kb) {
+      uint8_t* dst = smem + NST * stage_bytes + kb * raw_bytes;
+      mbar_expect_tx(raw_full + kb, raw_bytes);
+      tma_load_2d(dst, &map_a, raw_full + kb, kb * KB, (int)f0);
+      if (!TF32) tma_load_2d(dst + a_plane, &map_a, raw_full + kb, kb * KB + 32, (int)f0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    if (smem_base & 1023u) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   } else if (warp == 2) {
@@ -345,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer: weight hi/lo planes into the operand stages =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = pre_w; kb < nkb; ++kb) {
         const int s = kb % NST, ph = (kb / NST) & 1;
         mbar_wait(empty + s, ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
@@ -357,7 +379,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   } else if (warp == 3) {
     // ===== TMA producer: raw fp32 activation tiles [NF frames x 32 floats], rows past F are zero-filled =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = pre_r; kb < nkb; ++kb) {
         const int r = kb % RST, ph = (kb / RST) & 1;
         mbar_wait(raw_empty + r, ph ^ 1);
         uint8_t* dst = smem + NST * stage_bytes + r * raw_bytes;
