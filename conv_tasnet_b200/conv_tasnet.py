@@ -324,6 +324,17 @@ class ConvTasNet(nn.Module):
                 else:
                     p.grad += v
 
+    def _backward_stage(self, mixture, d_est, ws, stage):
+        """One stage of the staged backward straight into the flat gradient buffer (stage 0 zero-initialises it).
+        Used by graph.GraphedTrainStep, which captures one CUDA graph per stage so that the data-parallel all-reduce of
+        a finished slice overlaps the next stage's graph."""
+        M, T = mixture.shape
+        grads = self.flat_grads
+        with torch.cuda.device(mixture.device):
+            _lib.check(_lib.lib().ctn_model_backward_stage(
+                ctypes.byref(self._cfg), _lib.ptr(self._flat), _lib.ptr(mixture), M, T, _lib.ptr(d_est),
+                _lib.ptr(grads), _lib.ptr(ws), ws.numel(), 0, stage, _lib.stream()))
+
     def grad_bucket(self, stage):
         off, cnt = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(_lib.lib().ctn_grad_bucket(ctypes.byref(self._cfg), stage, ctypes.byref(off), ctypes.byref(cnt)))

@@ -6,20 +6,23 @@ replayed with a single graph launch; inputs are copied into the graph's static b
 when the caller hands over pinned host tensors)."""
 import torch
 
-from .pit_criterion import cal_loss
+from . import _lib
+from .pit_criterion import _pit_forward_raw, cal_loss
 
 
 class GraphedTrainStep:
     """step = GraphedTrainStep(model_or_dp, optimizer); loss = step(mixture, source, lengths)
 
     `optimizer` must be capturable (conv_tasnet_b200.optim.FusedAdam is).  Under data parallelism
-    (ShardedDataParallel) the collectives stay outside the graphs: graph 1 = forward + loss + backward, then the
-    bucketed NCCL all-reduce of the flat gradient buffer is launched eagerly, then graph 2 = clip + Adam.
-    Falls back to eager launches if capture is refused."""
+    (ShardedDataParallel) the collectives stay outside the graphs and overlap them: graph 0 = forward + PIT loss + its
+    gradient + backward stage 0, graphs 1..R+1 = the remaining backward stages; after each replay the finished slice of
+    the flat gradient buffer is all-reduced asynchronously on NCCL's stream while the next graph runs; the last graph
+    (clip + Adam) waits for the collectives.  Falls back to eager launches if capture is refused."""
 
     def __init__(self, model, optimizer, warmup=3):
         self.model, self.optimizer, self.warmup = model, optimizer, warmup
         self._shape, self._graph, self._graph2, self._static, self._loss = None, None, None, None, None
+        self._stage_graphs, self._keep = None, None
         self.captured = False
 
     def _fwd_bwd(self, mix, src, lens):
@@ -57,28 +60,53 @@ class GraphedTrainStep:
                 with torch.cuda.graph(g):
                     self._loss = self._eager(*self._static)
                 self._graph, self._graph2 = g, None
-            else:  # collectives stay eager, between two graphs
-                hook, dp.module._grad_sync = dp.module._grad_sync, None
-                try:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._loss = self._fwd_bwd(*self._static)
-                    g2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g2):
-                        self.optimizer.step()
-                finally:
-                    dp.module._grad_sync = hook
-                self._graph, self._graph2 = g, g2
+            else:  # collectives stay eager, between the per-stage graphs
+                self._capture_staged(dp)
             self.captured = True
         except Exception:  # capture refused: keep working, eagerly
             torch.cuda.synchronize(dev)
             self._graph, self._graph2, self.captured = None, None, False
         self._shape = (tuple(mix.shape), tuple(src.shape))
 
+    def _capture_staged(self, dp):
+        """forward + loss + backward as R+2 graphs cut at the gradient-bucket boundaries (driving the C ABI directly:
+        ctn_model_forward, ctn_pit_forward/backward, ctn_model_backward_stage), then the optimizer graph"""
+        m = dp.module
+        mix, src, lens = self._static
+        lens = lens.to(torch.int64)
+        L = _lib.lib()
+        pool = torch.cuda.graph_pool_handle()
+        if any(p.grad is None for p in m.parameters()):
+            for p, v in zip(m.parameters(), m.grad_views()):
+                p.grad = v
+        graphs = []
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            est, ws, token = m._run_forward(mix, training=True)
+            loss, _max_snr, _idx, coef, _ = _pit_forward_raw(src, est, lens, False)
+            d_est = torch.empty_like(est)
+            one = torch.ones(1, dtype=torch.float32, device=est.device)
+            B, C, T = src.shape
+            _lib.check(L.ctn_pit_backward(_lib.ptr(src), _lib.ptr(est), _lib.ptr(lens), _lib.ptr(coef), _lib.ptr(one),
+                                          B, C, T, _lib.ptr(d_est), _lib.stream()))
+            m._backward_stage(mix, d_est, ws, 0)
+        graphs.append(g)
+        for stage in range(1, m.R + 2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                m._backward_stage(mix, d_est, ws, stage)
+            graphs.append(g)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=pool):
+            self.optimizer.step()
+        self._keep = (est, ws, token, coef, d_est, one, lens)  # tensors the graphs reference
+        self._loss = loss.view(())
+        self._graph, self._graph2, self._stage_graphs = graphs[0], g2, graphs
+
     def __call__(self, mixture, source, lengths):
         if self._shape != (tuple(mixture.shape), tuple(source.shape)):
             self._capture(mixture.to(self._device_of(), non_blocking=True), source.to(self._device_of(), non_blocking=True),
-                          torch.as_tensor(lengths).to(self._device_of(), non_blocking=True))
+                          torch.as_tensor(lengths).to(device=self._device_of(), dtype=torch.int64, non_blocking=True))
         if self._graph is None:
             dev = self._device_of()
             return self._eager(mixture.to(dev, non_blocking=True), source.to(dev, non_blocking=True),
@@ -86,9 +114,14 @@ class GraphedTrainStep:
         for d, s in zip(self._static, (mixture, source, lengths)):
             if d.data_ptr() != (s.data_ptr() if isinstance(s, torch.Tensor) and s.is_cuda else -1):
                 d.copy_(torch.as_tensor(s), non_blocking=True)
-        self._graph.replay()
-        if self._graph2 is not None:
-            self._dp().all_reduce_flat()
+        if self._graph2 is None:
+            self._graph.replay()
+        else:
+            dp = self._dp()
+            for stage, g in enumerate(self._stage_graphs):
+                g.replay()
+                dp._on_stage(dp.module, stage)  # async all-reduce of the slice this stage finished
+            dp._on_stage(dp.module, -1)         # the current stream waits for the collectives
             self._graph2.replay()
         return self._loss
 

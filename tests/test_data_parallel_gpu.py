@@ -53,6 +53,28 @@ def _worker(rank, world, port, q):
     gathered = [torch.empty_like(g_dp) for _ in range(world)]
     dist.all_gather(gathered, g_dp)
     assert torch.equal(gathered[0], gathered[1])  # every replica ends with identical gradients
+    # the graph-replayed data-parallel step (one CUDA graph per backward stage, all-reduce overlapped between them)
+    # follows the eager data-parallel step parameter for parameter
+    from conv_tasnet_b200.graph import GraphedTrainStep
+    from conv_tasnet_b200.optim import FusedAdam
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
+    losses_e = []
+    for _ in range(3):
+        est = dp(m.contiguous())
+        loss, *_ = cal_loss(s.contiguous(), est, l.contiguous())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses_e.append(loss.item())
+    p_eager = model.flat_params.clone()
+    model.load_state_dict(sd0)
+    opt2 = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
+    step = GraphedTrainStep(dp, opt2, warmup=0)
+    losses_g = [step(m.contiguous(), s.contiguous(), l.contiguous()).item() for _ in range(3)]
+    assert step.captured and step._stage_graphs is not None and len(step._stage_graphs) == cfgd["R"] + 2
+    assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-4, (losses_e, losses_g)
+    assert ((model.flat_params - p_eager).abs().max() / p_eager.abs().max()).item() < 1e-5
     dist.barrier()
     dist.destroy_process_group()
 
