@@ -16,7 +16,7 @@ from typing import Dict, List
 
 import torch
 
-from .conv_tasnet_oracle import Config, EPS, permutations_of
+from .conv_tasnet_oracle import Config, EPS, is_batch_norm, permutations_of
 
 
 # ------------------------------------------------------------------ helpers
@@ -31,9 +31,10 @@ def dprelu(z, a):  # torch: grad passes where z > 0, alpha elsewhere (z == 0 tak
 def block_names(cfg: Config, r: int, x: int):
     p = f"separator.network.2.{r}.{x}.net."
     sh = 1 if cfg.causal else 0
-    return dict(W1=p + "0.weight", a1=p + "1.weight", g1=p + "2.gamma", b1=p + "2.beta",
+    gk, bk = ("weight", "bias") if is_batch_norm(cfg) else ("gamma", "beta")  # nn.BatchNorm1d names (:306-309)
+    return dict(W1=p + "0.weight", a1=p + "1.weight", g1=p + "2." + gk, b1=p + "2." + bk, n1=p + "2.",
                 Wd=p + "3.net.0.weight", a2=p + f"3.net.{1 + sh}.weight",
-                g2=p + f"3.net.{2 + sh}.gamma", b2=p + f"3.net.{2 + sh}.beta",
+                g2=p + f"3.net.{2 + sh}." + gk, b2=p + f"3.net.{2 + sh}." + bk, n2=p + f"3.net.{2 + sh}.",
                 W2=p + f"3.net.{3 + sh}.weight")
 
 
@@ -61,6 +62,47 @@ def sample_stats(a):
 
 def norm_stats(cfg, a):
     return sample_stats(a) if cfg.norm_type == "gLN" else row_stats(a)
+
+
+def bn_forward_stats(sd, prefix, a, training, momentum=0.1, eps=1e-5):
+    """BatchNorm branch (batchnorm.cu: bn_stats + bn_finalize): per-channel statistics of a [M,K,Ch] over (M,K) in
+    training (running statistics updated in place, unbiased variance) or the running statistics in evaluation
+    -> (mean, rstd, s, t) with n = s*a + t, s = weight*rstd, t = bias - mean*s."""
+    Ch = a.shape[2]
+    if training:
+        mean = a.mean(dim=(0, 1))
+        var = ((a - mean.view(1, 1, Ch)) ** 2).mean(dim=(0, 1))
+        n = a.shape[0] * a.shape[1]
+        with torch.no_grad():
+            sd[prefix + "running_mean"].mul_(1 - momentum).add_(momentum * mean.to(sd[prefix + "running_mean"].dtype))
+            sd[prefix + "running_var"].mul_(1 - momentum).add_(
+                momentum * (var * (n / max(n - 1, 1))).to(sd[prefix + "running_var"].dtype))
+            sd[prefix + "num_batches_tracked"] += 1
+    else:
+        mean, var = sd[prefix + "running_mean"].to(a.dtype), sd[prefix + "running_var"].to(a.dtype)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    s = sd[prefix + "weight"] * rstd
+    return mean, rstd, s, sd[prefix + "bias"] - mean * s
+
+
+def bn_bwd(dn, z, alpha, mean, rstd, weight, training):
+    """Backward of n = weight*(prelu(z)-mean)*rstd + bias through the batch statistics (bn_bwd_finalize + bn_bwd_apply):
+    A = sum dn, B = sum dn*p  ->  dweight = rstd (B - mean A), dbias = A,
+    dp = s (dn - A/F - (p - mean) rstd dweight / F) in training, s dn in evaluation.  -> dz, dweight, dbias, dalpha"""
+    Ch = z.shape[2]
+    p = prelu(z, alpha)
+    F_ = z.shape[0] * z.shape[1]
+    A = dn.sum(dim=(0, 1))
+    Bv = (dn * p).sum(dim=(0, 1))
+    dweight = rstd * (Bv - mean * A)
+    s = (weight * rstd).view(1, 1, Ch)
+    if training:
+        dp = s * (dn - (A / F_).view(1, 1, Ch) - (p - mean.view(1, 1, Ch)) * (rstd * dweight / F_).view(1, 1, Ch))
+    else:
+        dp = s * dn
+    dz = dp * dprelu(z, alpha)
+    dalpha = (dp * torch.where(z > 0, torch.zeros_like(z), z)).sum().view(1)
+    return dz, dweight, A, dalpha
 
 
 def gemm_normfold(a, mu, r, W, gamma, beta, res=None):
@@ -109,10 +151,13 @@ def decoder_fwd(cfg, score, w, V, T):
     return est
 
 
-def model_fwd(cfg: Config, sd: Dict[str, torch.Tensor], mix, keep=True):
-    """Whole forward in kernel order.  Returns est [M,C,T] and the stash the backward consumes."""
+def model_fwd(cfg: Config, sd: Dict[str, torch.Tensor], mix, keep=True, training=True):
+    """Whole forward in kernel order.  Returns est [M,C,T] and the stash the backward consumes.
+    BatchNorm branch: identity statistics (mu 0, r 1) with the per-channel (s, t) in place of (gamma, beta)."""
     T = mix.shape[1]
     st = {}
+    bn = is_batch_norm(cfg)
+    zero, one = mix.new_zeros(1, 1, 1), mix.new_ones(1, 1, 1)
     U = sd["encoder.conv1d_U.weight"][:, 0, :]
     w = encoder_fwd(mix, U)
     mu0, r0 = row_stats(w)
@@ -124,13 +169,24 @@ def model_fwd(cfg: Config, sd: Dict[str, torch.Tensor], mix, keep=True):
             nm = block_names(cfg, r, xi)
             d = 2 ** xi
             z1 = x @ sd[nm["W1"]][:, :, 0].t()
-            mu1, r1 = norm_stats(cfg, prelu(z1, sd[nm["a1"]]))
-            z2 = dwconv_fwd(cfg, z1, sd[nm["a1"]], mu1, r1, sd[nm["g1"]].view(-1), sd[nm["b1"]].view(-1),
-                            sd[nm["Wd"]][:, 0, :], d)
+            bn1 = bn2 = None
+            if bn:
+                bn1 = bn_forward_stats(sd, nm["n1"], prelu(z1, sd[nm["a1"]]), training)
+                mu1, r1, ga1, be1 = zero, one, bn1[2], bn1[3]
+            else:
+                mu1, r1 = norm_stats(cfg, prelu(z1, sd[nm["a1"]]))
+                ga1, be1 = sd[nm["g1"]].view(-1), sd[nm["b1"]].view(-1)
+            z2 = dwconv_fwd(cfg, z1, sd[nm["a1"]], mu1, r1, ga1, be1, sd[nm["Wd"]][:, 0, :], d)
             a2 = prelu(z2, sd[nm["a2"]])
-            mu2, r2 = norm_stats(cfg, a2)
-            out = gemm_normfold(a2, mu2, r2, sd[nm["W2"]][:, :, 0], sd[nm["g2"]].view(-1), sd[nm["b2"]].view(-1), res=x)
-            st["blocks"].append(dict(x=x, z1=z1, z2=z2, mu1=mu1, r1=r1, mu2=mu2, r2=r2, d=d, nm=nm))
+            if bn:
+                bn2 = bn_forward_stats(sd, nm["n2"], a2, training)
+                mu2, r2, ga2, be2 = zero, one, bn2[2], bn2[3]
+            else:
+                mu2, r2 = norm_stats(cfg, a2)
+                ga2, be2 = sd[nm["g2"]].view(-1), sd[nm["b2"]].view(-1)
+            out = gemm_normfold(a2, mu2, r2, sd[nm["W2"]][:, :, 0], ga2, be2, res=x)
+            st["blocks"].append(dict(x=x, z1=z1, z2=z2, mu1=mu1, r1=r1, mu2=mu2, r2=r2, d=d, nm=nm, bn1=bn1, bn2=bn2,
+                                     ga1=ga1, be1=be1, ga2=ga2, be2=be2, training=training))
             x = out
     score = x @ sd["separator.network.3.weight"][:, :, 0].t()
     st.update(y=x, score=score)
@@ -279,18 +335,26 @@ def model_bwd(cfg: Config, sd, mix, st, d_est):
         b = st["blocks"][bi]
         nm = b["nm"]
         W1, W2 = sd[nm["W1"]][:, :, 0], sd[nm["W2"]][:, :, 0]
-        g1, b1, g2, b2 = (sd[nm[k]].view(-1) for k in ("g1", "b1", "g2", "b2"))
+        bn = b["bn1"] is not None
+        g1, b1, g2, b2 = b["ga1"], b["be1"], b["ga2"], b["be2"]  # (gamma, beta), or BatchNorm's (s, t)
         a1, a2 = sd[nm["a1"]], sd[nm["a2"]]
         H = W1.shape[0]
+        gshape = (H,) if bn else (1, H, 1)
         dn2 = g @ W2
         n2 = g2.view(1, 1, H) * (prelu(b["z2"], a2) - b["mu2"]) * b["r2"] + b2.view(1, 1, H)
         G[nm["W2"]] = torch.einsum("mko,mkh->oh", g, n2).unsqueeze(2)
-        dz2, dg2, db2, da2 = norm_bwd(cfg, dn2, b["z2"], a2, b["mu2"], b["r2"], g2)
-        G[nm["g2"]], G[nm["b2"]], G[nm["a2"]] = dg2.view(1, H, 1), db2.view(1, H, 1), da2
+        if bn:
+            dz2, dg2, db2, da2 = bn_bwd(dn2, b["z2"], a2, b["bn2"][0], b["bn2"][1], sd[nm["g2"]], b["training"])
+        else:
+            dz2, dg2, db2, da2 = norm_bwd(cfg, dn2, b["z2"], a2, b["mu2"], b["r2"], g2)
+        G[nm["g2"]], G[nm["b2"]], G[nm["a2"]] = dg2.view(gshape), db2.view(gshape), da2
         dn1, dWd = dwconv_bwd(cfg, dz2, b["z1"], a1, b["mu1"], b["r1"], g1, b1, sd[nm["Wd"]][:, 0, :], b["d"])
         G[nm["Wd"]] = dWd.unsqueeze(1)
-        dz1, dg1, db1, da1 = norm_bwd(cfg, dn1, b["z1"], a1, b["mu1"], b["r1"], g1)
-        G[nm["g1"]], G[nm["b1"]], G[nm["a1"]] = dg1.view(1, H, 1), db1.view(1, H, 1), da1
+        if bn:
+            dz1, dg1, db1, da1 = bn_bwd(dn1, b["z1"], a1, b["bn1"][0], b["bn1"][1], sd[nm["g1"]], b["training"])
+        else:
+            dz1, dg1, db1, da1 = norm_bwd(cfg, dn1, b["z1"], a1, b["mu1"], b["r1"], g1)
+        G[nm["g1"]], G[nm["b1"]], G[nm["a1"]] = dg1.view(gshape), db1.view(gshape), da1
         G[nm["W1"]] = torch.einsum("mkh,mkb->hb", dz1, b["x"]).unsqueeze(2)
         g = g + dz1 @ W1
     # bottleneck + first cLN
@@ -307,8 +371,8 @@ def model_bwd(cfg: Config, sd, mix, st, d_est):
     return G
 
 
-def train_step(cfg, sd, mix, src, lengths):
-    est, st = model_fwd(cfg, sd, mix)
+def train_step(cfg, sd, mix, src, lengths, training=True):
+    est, st = model_fwd(cfg, sd, mix, training=training)
     pf = pit_fwd(src, est, lengths)
     d_est = pit_bwd(src, pf["est_masked"], pf)
     return pf, est, model_bwd(cfg, sd, mix, st, d_est)

@@ -36,6 +36,36 @@ def test_fused_schedule_equals_oracle(name, dtype, tol_out, tol_grad):
         assert rel_err(grads[k], z["g:" + k]) < 1e-3, k
 
 
+@pytest.mark.parametrize("name", ["bn", "bn_causal_c3"])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_schedule_batchnorm_branch(name, training):
+    """BatchNorm as the kernels compute it (identity statistics + per-channel (s, t); backward from the per-channel
+    sums A, B) equals nn.BatchNorm1d semantics of the op-by-op oracle in fp64: outputs, every gradient, and the
+    running statistics left behind; and the reference's fp32 vectors."""
+    cfgd, sd, z = golden_model(name)
+    cfg = O.Config(**cfgd)
+    to64 = lambda d: {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in d.items()}
+    mix = torch.from_numpy(z["mixture"]).double()
+    src = torch.from_numpy(z["source"]).double()
+    lens = torch.from_numpy(z["lengths"])
+    sd_o, sd_f = to64(sd), to64(sd)
+    loss_o, est_o, grads_o, _, _ = O.train_step_grads(cfg, sd_o, mix, src, lens, training=training)
+    pf, est, grads = FS.train_step(cfg, sd_f, mix, src, lens, training=training)
+    assert rel_err(pf["est_masked"], est_o) < 1e-10
+    assert abs(pf["loss"].item() - loss_o.item()) < 1e-8
+    assert set(grads) == set(grads_o)
+    for k in grads_o:
+        assert grads[k].shape == grads_o[k].shape, k
+        assert rel_err(grads[k], grads_o[k]) < 1e-8, k
+    for k in sd_o:
+        if O.is_buffer(k):
+            assert rel_err(sd_f[k], sd_o[k]) < 1e-12, k
+    pre = "g:" if training else "ge:"
+    assert rel_err(est, z["est_source" if training else "eval_est_source"]) < 1e-4
+    errs = sorted(rel_err(grads[k], z[pre + k]) for k in grads_o)
+    assert errs[len(errs) // 2] < 1e-4 and errs[-1] < 5e-3
+
+
 def test_pit_moments_form_matches_reference_cases():
     z = load_golden("pit.npz")
     for i in range(int(z["n_cases"])):
