@@ -92,9 +92,10 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
 //   evaluation: dp = s dn  (the statistics are constants)
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ A, const float* __restrict__ Bv,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                              const float* __restrict__ mode, int64_t F, int C,
-                                                              float* __restrict__ dweight, float* __restrict__ dbias,
-                                                              float* __restrict__ ca, float* __restrict__ cq) {
+                                                              const float* __restrict__ mode, int mode_override,
+                                                              int64_t F, int C, float* __restrict__ dweight,
+                                                              float* __restrict__ dbias, float* __restrict__ ca,
+                                                              float* __restrict__ cq) {
   pdl_launch_dependents();
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   const float a = A[c], dw = rstd[c] * (Bv[c] - mean[c] * a);
   dbias[c] += a;
   dweight[c] += dw;
-  const bool batch = mode[0] != 0.f;
+  const bool batch = mode_override >= 0 ? mode_override != 0 : mode[0] != 0.f;
   ca[c] = batch ? a / (float)F : 0.f;
   cq[c] = batch ? rstd[c] * dw / (float)F : 0.f;
 }
@@ -180,8 +181,10 @@ int run_bn_forward_stats(const float* z, const float* alpha, const float* weight
 }
 
 int run_bn_bwd_finalize(const float* A, const float* Bv, const float* mean, const float* rstd, const float* mode,
-                        int64_t F, int C, float* dweight, float* dbias, float* ca, float* cq, cudaStream_t s) {
-  launch_kernel(bn_bwd_finalize_kernel, cdiv(C, 256), 256, 0, s, A, Bv, mean, rstd, mode, F, C, dweight, dbias, ca, cq);
+                        int mode_override, int64_t F, int C, float* dweight, float* dbias, float* ca, float* cq,
+                        cudaStream_t s) {
+  launch_kernel(bn_bwd_finalize_kernel, cdiv(C, 256), 256, 0, s, A, Bv, mean, rstd, mode, mode_override, F, C, dweight,
+                dbias, ca, cq);
   return check_launch("bn_bwd_finalize_kernel");
 }
 

@@ -33,6 +33,13 @@ int run_adam_step(float*, const float*, float*, float*, int64_t, float, float, f
 int run_assemble_batch(const float*, const float*, const int64_t*, int, int, int, float*, float*, int64_t*, cudaStream_t);
 int run_pack_valid(const float*, const int64_t*, const int64_t*, int, int, int, float*, cudaStream_t);
 
+int run_bn_forward_stats(const float*, const float*, const float*, const float*, float*, float*, int64_t, int, int, double*,
+                         float*, float*, float*, float*, float*, cudaStream_t);
+int run_bn_bwd_finalize(const float*, const float*, const float*, const float*, const float*, int, int64_t, int, float*,
+                        float*, float*, float*, cudaStream_t);
+int run_bn_bwd_apply(float*, const float*, const float*, const float*, const float*, const float*, const float*, int64_t,
+                     int, float*, cudaStream_t);
+
 static NormStats make_stats(const double* gln_acc, const float* rowstat, int K, int Ch) {
   NormStats st;
   st.acc = gln_acc;
@@ -169,6 +176,27 @@ int32_t ctn_norm_bwd_apply(float* dn, const float* z, const float* alpha, const 
                            cudaStream_t stream) {
   CTN_REQUIRE(rowstat != nullptr || (gln_acc != nullptr && red != nullptr), "norm_bwd_apply: gLN needs gln_acc and red");
   return run_norm_bwd_apply(dn, z, alpha, make_stats(gln_acc, rowstat, K, Ch), gamma, red, M, K, Ch, dalpha, stream);
+}
+
+int32_t ctn_batchnorm_stats(const float* z, const float* alpha, const float* weight, const float* bias, float* running_mean,
+                            float* running_var, int64_t F, int32_t C, int32_t batch_stats, void* scratch, float* mean,
+                            float* rstd, float* s, float* t, cudaStream_t stream) {
+  CTN_REQUIRE(z && weight && bias && scratch && mean && rstd && s && t, "batchnorm_stats: null pointer");
+  double* acc = reinterpret_cast<double*>(scratch);
+  float* mode = reinterpret_cast<float*>(acc + 2 * (int64_t)C);
+  if (batch_stats) CTN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, stream));
+  return run_bn_forward_stats(z, alpha, weight, bias, running_mean, running_var, F, C, batch_stats ? 1 : 0, acc, mean, rstd,
+                              s, t, mode, stream);
+}
+
+int32_t ctn_batchnorm_bwd(float* dn, const float* z, const float* alpha, const float* A, const float* Bsum,
+                          const float* mean, const float* rstd, const float* s, int32_t batch_stats, int64_t F, int32_t C,
+                          float* dweight, float* dbias, float* dalpha, void* scratch, cudaStream_t stream) {
+  CTN_REQUIRE(dn && z && A && Bsum && mean && rstd && s && dweight && dbias && scratch, "batchnorm_bwd: null pointer");
+  float* ca = reinterpret_cast<float*>(scratch);
+  float* cq = ca + C;
+  CTN_TRY(run_bn_bwd_finalize(A, Bsum, mean, rstd, nullptr, batch_stats ? 1 : 0, F, C, dweight, dbias, ca, cq, stream));
+  return run_bn_bwd_apply(dn, z, alpha, s, mean, ca, cq, F, C, dalpha, stream);
 }
 
 int32_t ctn_decoder_fwd(const float* score, const float* w, const float* V, int32_t M, int32_t K, int32_t C, int32_t N,

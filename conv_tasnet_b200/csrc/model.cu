@@ -95,8 +95,8 @@ int run_decoder_bwd(const float*, const float*, const float*, const float*, int,
 
 int run_bn_forward_stats(const float*, const float*, const float*, const float*, float*, float*, int64_t, int, int, double*,
                          float*, float*, float*, float*, float*, cudaStream_t);
-int run_bn_bwd_finalize(const float*, const float*, const float*, const float*, const float*, int64_t, int, float*, float*,
-                        float*, float*, cudaStream_t);
+int run_bn_bwd_finalize(const float*, const float*, const float*, const float*, const float*, int, int64_t, int, float*,
+                        float*, float*, float*, cudaStream_t);
 int run_bn_bwd_apply(float*, const float*, const float*, const float*, const float*, const float*, const float*, int64_t,
                      int, float*, cudaStream_t);
 
@@ -535,7 +535,7 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
                                 dalpha, s);
     // BatchNorm: the folded per-channel sums -> dweight, dbias and the coefficients of the apply pass
     CTN_TRY(run_bn_bwd_finalize(X.bn_ab(b, which, 0), X.bn_ab(b, which, 1), X.bn_fwd(b, which, 0), X.bn_fwd(b, which, 1),
-                                X.bn_mode(b, which), F, c.H, gblk(b, which ? L.g2 : L.g1), gblk(b, which ? L.b2 : L.b1),
+                                X.bn_mode(b, which), -1, F, c.H, gblk(b, which ? L.g2 : L.g1), gblk(b, which ? L.b2 : L.b1),
                                 X.bn_coef(b, which, 0), X.bn_coef(b, which, 1), s));
     return run_bn_bwd_apply(dn, z, alpha, X.bn_fwd(b, which, 2), X.bn_fwd(b, which, 0), X.bn_coef(b, which, 0),
                             X.bn_coef(b, which, 1), F, c.H, dalpha, s);

@@ -189,6 +189,20 @@ int32_t ctn_norm_bwd_reduce(const float* dn, const float* z, const float* alpha,
 int32_t ctn_norm_bwd_apply(float* dn, const float* z, const float* alpha, const double* gln_acc,
                            const float* rowstat, const float* gamma, const double* red, int32_t M,
                            int32_t K, int32_t Ch, float* dalpha, cudaStream_t stream);
+/* BatchNorm branch (chose_norm fall-through, src/conv_tasnet.py:306-309), statistics: z [F,C] (F = M*K frames),
+ * p = prelu(z, alpha) -> per-channel mean, rstd (eps 1e-5) and the affine map n = s*p + t (s = weight*rstd,
+ * t = bias - mean*s).  batch_stats != 0: statistics of this batch over all F frames, running_mean / running_var (may be
+ * NULL) updated with momentum 0.1 and the unbiased variance; batch_stats == 0: the running statistics.
+ * scratch: >= 16*C + 16 bytes. */
+int32_t ctn_batchnorm_stats(const float* z, const float* alpha, const float* weight, const float* bias,
+                            float* running_mean, float* running_var, int64_t F, int32_t C, int32_t batch_stats,
+                            void* scratch, float* mean, float* rstd, float* s, float* t, cudaStream_t stream);
+/* ... backward: dn (gradient w.r.t. n) -> dz IN PLACE through the norm (and the batch statistics when batch_stats != 0)
+ * and the PReLU; A = sum_f dn, Bsum = sum_f dn*p per channel (ctn_norm_bwd_reduce with gln_acc = rowstat = NULL returns
+ * them as dbeta / dgamma); dweight, dbias [C] and dalpha [1] accumulate.  scratch: >= 8*C bytes. */
+int32_t ctn_batchnorm_bwd(float* dn, const float* z, const float* alpha, const float* A, const float* Bsum,
+                          const float* mean, const float* rstd, const float* s, int32_t batch_stats, int64_t F,
+                          int32_t C, float* dweight, float* dbias, float* dalpha, void* scratch, cudaStream_t stream);
 /* mask nonlinearity * w -> basis -> overlap-add -> pad (src/conv_tasnet.py:208-214,140-145,57-59):
  * score [M,K,C*N], w [M,K,N], V [L,N] -> est [M,C,T] */
 int32_t ctn_decoder_fwd(const float* score, const float* w, const float* V, int32_t M, int32_t K, int32_t C,

@@ -182,6 +182,43 @@ def test_norm_bwd(norm, prelu, M, K, Ch):
         assert abs(dalpha.item() - w_da.item()) < TOL_G * max(1.0, abs(w_da.item()), w_dz.abs().sum().item() * 1e-3)
 
 
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("M,K,Ch", [(2, 99, 16), (3, 700, 512), (1, 33, 20)])
+def test_batchnorm_stats_and_backward(training, M, K, Ch):
+    """BatchNorm branch kernels (bn_stats / bn_finalize / bn_bwd_finalize / bn_bwd_apply + the shared per-channel
+    reduction) against oracle/fused_schedule.py::bn_forward_stats / bn_bwd"""
+    z, dn = rnd(M, K, Ch, seed=31) + 0.1, rnd(M, K, Ch, seed=32)
+    weight, bias = rnd(Ch, seed=33).abs() + 0.5, rnd(Ch, seed=34)
+    rm, rv = 0.05 * rnd(Ch, seed=35), rnd(Ch, seed=36).abs() + 0.3
+    alpha = torch.tensor([0.35], device=dev())
+    F = M * K
+    sd = {"n.weight": weight.cpu().double(), "n.bias": bias.cpu().double(), "n.running_mean": rm.cpu().double().clone(),
+          "n.running_var": rv.cpu().double().clone(), "n.num_batches_tracked": torch.zeros((), dtype=torch.int64)}
+    a = FS.prelu(z.cpu().double(), 0.35)
+    w_mean, w_rstd, w_s, w_t = FS.bn_forward_stats(sd, "n.", a, training)
+    mean, rstd, s, t = (torch.empty(Ch, device=dev()) for _ in range(4))
+    scratch = torch.empty(16 * Ch + 16, dtype=torch.uint8, device=dev())
+    rm_d, rv_d = rm.clone(), rv.clone()
+    call("ctn_batchnorm_stats", P(z), P(alpha), P(weight), P(bias), P(rm_d), P(rv_d), F, Ch, 1 if training else 0,
+         P(scratch), P(mean), P(rstd), P(s), P(t))
+    for got, want in ((mean, w_mean), (rstd, w_rstd), (s, w_s), (t, w_t), (rm_d, sd["n.running_mean"]),
+                      (rv_d, sd["n.running_var"])):
+        assert rel_err(got.cpu(), want) < TOL_F
+    # backward: per-channel sums through the shared reduction kernel (no statistics = identity), then finalize + apply
+    A, Bs = torch.zeros(Ch, device=dev()), torch.zeros(Ch, device=dev())
+    call("ctn_norm_bwd_reduce", P(dn), P(z), P(alpha), None, None, P(s), M, K, Ch, P(Bs), P(A), None)
+    dw, db, dalpha = torch.zeros(Ch, device=dev()), torch.zeros(Ch, device=dev()), torch.zeros(1, device=dev())
+    dz = dn.clone()
+    call("ctn_batchnorm_bwd", P(dz), P(z), P(alpha), P(A), P(Bs), P(mean), P(rstd), P(s), 1 if training else 0, F, Ch,
+         P(dw), P(db), P(dalpha), P(scratch))
+    w_dz, w_dw, w_db, w_da = FS.bn_bwd(dn.cpu().double(), z.cpu().double(), torch.tensor(0.35, dtype=torch.float64),
+                                       w_mean, w_rstd, weight.cpu().double(), training)
+    assert rel_err(dz.cpu(), w_dz) < TOL_G
+    assert rel_err(dw.cpu(), w_dw) < TOL_G
+    assert rel_err(db.cpu(), w_db) < TOL_G
+    assert abs(dalpha.item() - w_da.item()) < TOL_G * max(1.0, abs(w_da.item()), w_dz.abs().sum().item() * 1e-3)
+
+
 @pytest.mark.parametrize("softmax", [0, 1])
 @pytest.mark.parametrize("M,K,C,N,L,pad", [(2, 99, 2, 16, 8, 3), (3, 3199, 2, 256, 20, 0), (2, 64, 3, 12, 6, 5),
                                             (1, 40, 2, 8, 5, 0), (2, 33, 4, 8, 4, 1)])
