@@ -28,7 +28,8 @@ def cfg_of(**kw):
     return O.Config(**base)
 
 
-@pytest.mark.parametrize("M,T,N,L", [(2, 403, 16, 8), (3, 32000, 256, 20), (1, 131, 8, 4), (2, 100, 12, 5)])
+@pytest.mark.parametrize("M,T,N,L", [(2, 403, 16, 8), (3, 32000, 256, 20), (1, 131, 8, 4), (2, 100, 12, 5),
+                                     (2, 2000, 512, 32), (1, 1000, 320, 20)])
 def test_encoder_fwd_bwd(M, T, N, L):
     mix, U = rnd(M, T, seed=1, scale=0.1), rnd(N, L, seed=2, scale=0.3)
     K = O.n_frames(T, L)
@@ -221,7 +222,8 @@ def test_batchnorm_stats_and_backward(training, M, K, Ch):
 
 @pytest.mark.parametrize("softmax", [0, 1])
 @pytest.mark.parametrize("M,K,C,N,L,pad", [(2, 99, 2, 16, 8, 3), (3, 3199, 2, 256, 20, 0), (2, 64, 3, 12, 6, 5),
-                                            (1, 40, 2, 8, 5, 0), (2, 33, 4, 8, 4, 1)])
+                                            (1, 40, 2, 8, 5, 0), (2, 33, 4, 8, 4, 1), (2, 150, 4, 512, 32, 2),
+                                            (1, 77, 3, 320, 20, 0), (2, 500, 2, 256, 32, 7)])
 def test_decoder_fwd_bwd(softmax, M, K, C, N, L, pad):
     cfg = cfg_of(C=C, N=N, L=L, mask_nonlinear="softmax" if softmax else "relu")
     S = L // 2
