@@ -30,6 +30,9 @@ class ShardedDataParallel(nn.Module):
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s weights (once; DataParallel re-broadcasts every step)."""
         dist.broadcast(self.module.flat_params, src=src, group=self.process_group)
+        if getattr(self.module, "_bns", None):  # BatchNorm branch: running statistics and batch counters too
+            dist.broadcast(self.module._bn_state, src=src, group=self.process_group)
+            dist.broadcast(self.module._bn_count, src=src, group=self.process_group)
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)

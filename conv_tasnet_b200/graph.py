@@ -65,7 +65,7 @@ class GraphedTrainStep:
             self.captured = True
         except Exception:  # capture refused: keep working, eagerly
             torch.cuda.synchronize(dev)
-            self._graph, self._graph2, self.captured = None, None, False
+            self._graph, self._graph2, self._stage_graphs, self.captured = None, None, None, False
         self._shape = (tuple(mix.shape), tuple(src.shape))
 
     def _capture_staged(self, dp):
