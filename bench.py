@@ -331,8 +331,8 @@ def main():
     roofline = {"kernel": "tc_wgrad_kernel<256>: dW[512,256] = dz1[F,512]^T x[F,256] (tcgen05, bf16x3 split, MN-major "
                 "operands, split-K + coalesced red.v4), the largest single kernel of the step (2 per TemporalBlock + 2)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                "traffic": 30054912, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per "
-                "launch (profiles/r1_final_wgrad_full_raw.csv); algorithmic input 29.5 MB",
+                "traffic": 30042112, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per "
+                "launch (profiles/r1b_wgrad_full_raw.csv); algorithmic input 29.5 MB",
                 "peak_source": pk_src + ", bf16 burst (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the "
                 "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops,
                 "launches_per_step": 2 * PAPER["R"] * PAPER["X"] + 2,
