@@ -97,17 +97,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // The same MMAs with the shared-memory descriptors passed as (low word, shared high word): the high word (SBO, version,
 // swizzle mode) never changes and the low word is (addr >> 4) | (LBO >> 4) << 16, so stepping along K is one IADD.
 __device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
@@ -235,7 +224,6 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 #define CTN_CONV_THREADS 256
 #endif
 constexpr int CONV_THREADS = CTN_CONV_THREADS;  // converter / epilogue threads (8 or 16 warps)
-constexpr int TC_THREADS = 128 + CONV_THREADS;  // + 4 control warps
 #ifndef CTN_CONV_THREADS_BF16
 #define CTN_CONV_THREADS_BF16 512
 #endif
@@ -679,7 +667,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 constexpr int WK = 32;       // f rows per stage
 constexpr int WSTAGES = 4;
-constexpr int WNI = 256;     // N tile (input channels); I must be a multiple of it or equal 128 (template below)
 
 struct TcWgradArgs {
   const float* G;    // [F, O]
