@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 
 // apply pass, gLN: dz = r*(dn*gamma - m1 - yhat*m2) * prelu'(z); dalpha += sum da * z * [z<=0]
 #ifndef CTN_GA_TK
-#define CTN_GA_TK 8
+#define CTN_GA_TK 16
 #endif
 constexpr int GA_TK = CTN_GA_TK;
 #ifndef CTN_GA_U
