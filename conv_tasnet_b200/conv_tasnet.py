@@ -106,6 +106,8 @@ class _ConvTasNetFn(torch.autograd.Function):
     def forward(ctx, model, mixture, _anchor):
         est, ws, token = model._run_forward(mixture, training=True)
         ctx.model, ctx.ws, ctx.token = model, ws, token
+        # data parallel with uneven shards: world * M_local / M_global, set by ShardedDataParallel.forward
+        ctx.scale, model._grad_scale = model._grad_scale, None
         ctx.save_for_backward(mixture)
         return est
 
@@ -113,6 +115,8 @@ class _ConvTasNetFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_est):
         (mixture,) = ctx.saved_tensors
+        if ctx.scale is not None:
+            d_est = d_est * ctx.scale
         ctx.model._run_backward(mixture, d_est.contiguous(), ctx.ws)
         ctx.ws = ctx.token = None
         return None, None, None
@@ -141,8 +145,10 @@ class ConvTasNet(nn.Module):
         self._flat = None
         self._flat_grad = None
         self._layout = None
-        self._ws_cache = {}
+        self._ws_cache = {}       # training flag -> (grow-only workspace, weakref of the autograd token using it)
+        self._ws_override = None  # set by graph.GraphedTrainStep / GraphedInference: the graph owns its workspace
         self._grad_sync = None  # set by data_parallel.ShardedDataParallel
+        self._grad_scale = None  # set per forward by ShardedDataParallel (uneven shards), consumed by the backward
         self._overwrite_next = False  # set by optim.FusedAdam: the next backward overwrites the flat gradients
         self._plist = None
         # BatchNorm branch: running statistics of every nn.BatchNorm1d in ONE flat buffer (the C ABI's norm_state)
@@ -232,20 +238,35 @@ class ConvTasNet(nn.Module):
         return [fg[o:o + n].view(p.shape) for p, o, n in zip(self._plist, offs, nums)]
 
     # ------------------------------------------------------------------ forward / backward plumbing
-    def _workspace(self, M, T, training):
-        """-> (workspace, is_the_cached_one).  The cached workspace of a shape is reused unless an autograd graph
-        still holds its activation stash (its token is alive); then a temporary one is allocated."""
-        key = (M, T, bool(training))
-        entry = self._ws_cache.get(key)
-        if entry is not None:
-            ws, tok_ref = entry
-            if tok_ref is None or tok_ref() is None:
-                return ws, True
+    def workspace_bytes(self, M, T, training):
         nbytes = _lib.lib().ctn_workspace_bytes(ctypes.byref(self._cfg), M, T, 1 if training else 0)
         if nbytes < 0:
             _lib.check(1)
+        return nbytes
+
+    def _workspace(self, M, T, training):
+        """-> (workspace, is_the_cached_one).
+
+        ONE grow-only workspace per `training` flag, reused for every (M, T) that fits (the reference's loops feed
+        variable-length batches: src/solver.py:183-188 cross-validation, src/evaluate.py:44, src/separate.py:44 — a
+        workspace per distinct shape would pin memory until OOM).  While an autograd graph still holds the cached
+        workspace's activation stash (its token is alive) a temporary one is allocated instead.  CUDA-graph wrappers
+        own their workspace and pass it through `_ws_override`."""
+        nbytes = self.workspace_bytes(M, T, training)
+        if self._ws_override is not None:
+            if self._ws_override.numel() < nbytes:
+                raise RuntimeError("graph-owned workspace is too small for this shape")
+            return self._ws_override, False
+        key = bool(training)
+        entry = self._ws_cache.get(key)
+        busy = entry is not None and entry[1] is not None and entry[1]() is not None
+        if entry is not None and not busy and entry[0].numel() >= nbytes:
+            return entry[0], True
+        if entry is not None and not busy:
+            self._ws_cache.pop(key)  # too small: release it before the larger allocation
+            del entry
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device)
-        if entry is None:
+        if not busy:
             self._ws_cache[key] = (ws, None)
             return ws, True
         return ws, False
@@ -283,7 +304,7 @@ class ConvTasNet(nn.Module):
         if training:
             token = _Token()
             if cached:
-                self._ws_cache[(M, T, True)] = (ws, weakref.ref(token))
+                self._ws_cache[True] = (ws, weakref.ref(token))
         return est, ws, token
 
     def _run_backward(self, mixture, d_est, ws):
@@ -304,8 +325,13 @@ class ConvTasNet(nn.Module):
         args = (ctypes.byref(self._cfg), _lib.ptr(self._flat), _lib.ptr(mixture), M, T, _lib.ptr(d_est),
                 _lib.ptr(target), _lib.ptr(ws), ws.numel(), accumulate)
         with torch.cuda.device(mixture.device):
-            if self._grad_sync is None or target is not grads:
+            if self._grad_sync is None:
                 _lib.check(L.ctn_model_backward(*args, _lib.stream()))
+            elif target is not grads:
+                # mixed ownership of .grad under data parallelism: the gradients computed aside are all-reduced as one
+                # buffer before they are added to the user's tensors (the replicas must not diverge)
+                _lib.check(L.ctn_model_backward(*args, _lib.stream()))
+                self._grad_sync(self, -2, target)
             else:
                 for stage in range(self.R + 2):
                     _lib.check(L.ctn_model_backward_stage(*args, stage, _lib.stream()))

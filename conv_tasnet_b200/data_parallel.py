@@ -3,8 +3,13 @@
 One process per GPU (torchrun), every rank holds the full weights and optimizer state and works on its own shard of
 the batch (gLN/cLN/PIT are per-sample, so sharding is exact).  The only exchange per step is the gradient
 all-reduce: the hand-written backward runs in R+2 stages (ctn_model_backward_stage), each finishing one contiguous
-slice of the flat gradient buffer, and every finished slice is all-reduced (NCCL over NVLink/NVSwitch, AVG) on
-NCCL's stream while the next stage computes.  No parameter broadcast per step, no hub GPU.
+slice of the flat gradient buffer, and every finished slice is all-reduced (NCCL over NVLink/NVSwitch) on NCCL's stream
+while the next stage computes.  No parameter broadcast per step, no hub GPU.
+
+Uneven shards (the reference's batches vary in size, src/data.py:84-108): every rank's loss is the mean over its OWN
+items, so the global-batch-mean gradient is sum_r (M_r / M_global) g_r.  The wrapper all-reduces the local batch size
+(4 bytes, asynchronous, no host sync) in every training forward and scales the incoming d_est of the model's backward
+by world * M_r / M_global on the device; the AVG all-reduce of the gradients then yields exactly that weighted sum.
 
 The wrapper exposes `.module`, `__call__`, `.parameters()`, `.train()/.eval()`, `.cuda()` so the reference's
 solver.py (which expects a DataParallel-style object, solver.py:61,97,141,188,194) runs unchanged.
@@ -15,11 +20,12 @@ import torch.nn as nn
 
 
 class ShardedDataParallel(nn.Module):
-    def __init__(self, module, process_group=None, overlap=True, broadcast_parameters=True):
+    def __init__(self, module, process_group=None, overlap=True, broadcast_parameters=True, weight_by_batch=True):
         super().__init__()
         self.module = module
         self.process_group = process_group
         self.overlap = overlap
+        self.weight_by_batch = weight_by_batch
         self._pending = []
         self._enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         if self._enabled:
@@ -34,23 +40,42 @@ class ShardedDataParallel(nn.Module):
             dist.broadcast(self.module._bn_state, src=src, group=self.process_group)
             dist.broadcast(self.module._bn_count, src=src, group=self.process_group)
 
+    def grad_scale_for(self, m_local, device):
+        """world * M_local / M_global as a 1-element device tensor (no host sync): the factor that turns the AVG
+        all-reduce of per-rank batch-mean gradients into the gradient of the GLOBAL batch mean."""
+        world = dist.get_world_size(self.process_group)
+        total = torch.full((1,), float(m_local), dtype=torch.float32, device=device)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.process_group)
+        return (float(m_local) * world) / total
+
     def forward(self, *inputs, **kwargs):
+        if self._enabled and self.weight_by_batch and torch.is_grad_enabled() and inputs:
+            x = inputs[0]
+            if x.shape[0] < 1:
+                raise ValueError("ShardedDataParallel: this rank's shard is empty; every rank needs at least one item "
+                                 "(shard_batch refuses such splits on all ranks)")
+            self.module._grad_scale = self.grad_scale_for(x.shape[0], x.device)
         return self.module(*inputs, **kwargs)
 
-    # called by ConvTasNet._run_backward after each backward stage (stage >= 0) and once to drain (stage == -1)
-    def _on_stage(self, model, stage):
-        if stage >= 0:
+    # called by ConvTasNet._run_backward after each backward stage (stage >= 0), once to drain (stage == -1), and with
+    # stage == -2 + an explicit buffer from the slow path (gradients computed aside): synchronous whole-buffer reduce
+    def _on_stage(self, model, stage, buf=None):
+        if stage == -2:
+            self._reduce(buf)
+            self._drain()
+        elif stage >= 0:
             off, cnt = model.grad_bucket(stage)
-            work = dist.all_reduce(model.flat_grads[off:off + cnt], op=dist.ReduceOp.AVG if _has_avg(model.flat_grads)
-                                   else dist.ReduceOp.SUM, group=self.process_group, async_op=True)
-            if not _has_avg(model.flat_grads):
-                self._pending.append((work, model.flat_grads[off:off + cnt]))
-            else:
-                self._pending.append((work, None))
+            self._reduce(model.flat_grads[off:off + cnt])
             if not self.overlap:
                 self._drain()
         else:
             self._drain()
+
+    def _reduce(self, view):
+        avg = _has_avg(view, self.process_group)
+        work = dist.all_reduce(view, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.process_group,
+                               async_op=True)
+        self._pending.append((work, None if avg else view))
 
     def _drain(self):
         world = dist.get_world_size(self.process_group)
@@ -69,15 +94,24 @@ class ShardedDataParallel(nn.Module):
         self._drain()
 
 
-def _has_avg(t):
-    return t.is_cuda  # NCCL implements AVG; gloo (CPU tests) does not
+def _has_avg(t, group=None):
+    return t.is_cuda and dist.get_backend(group) == "nccl"  # NCCL implements AVG; gloo does not
+
+
+def shard_sizes(n, world):
+    """Items per rank for a batch of n: as even as possible, larger shards first (like torch.chunk's scatter in
+    nn.DataParallel).  Raises on every rank alike when some rank would get nothing."""
+    if n < world:
+        raise ValueError(f"cannot shard a batch of {n} over {world} ranks: every rank needs at least one item")
+    base, extra = divmod(n, world)
+    return [base + (1 if r < extra else 0) for r in range(world)]
 
 
 def shard_batch(rank, world, *tensors):
     """Contiguous dim-0 shard of each tensor for this rank (the scatter DataParallel did inside forward)."""
     out = []
     for t in tensors:
-        n = t.shape[0]
-        per = (n + world - 1) // world
-        out.append(t[rank * per:min(n, (rank + 1) * per)])
+        sizes = shard_sizes(t.shape[0], world)
+        start = sum(sizes[:rank])
+        out.append(t[start:start + sizes[rank]])
     return out
