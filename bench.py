@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """bench.py — audio-seconds separated per second on B200 for the Conv-TasNet hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode train|fwd]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 0..4] [--mode train|fwd]
 
-Workload (BASELINE.json configs[1]): paper config N=256 L=20 B=256 H=512 P=3 X=8 R=4 C=2 gLN non-causal, batch 3 per
-GPU x 4 s segments @ 8 kHz, one training step = forward + PIT SI-SNR loss + backward (+ gradient all-reduce when N>1)
-+ clip_grad_norm_(5) + Adam — the body of the reference's hot loop (src/solver.py:188-196).  Synthetic 8 kHz mixtures,
-reference-default random init.  One JSON line on stdout (rank 0).
+Workloads = BASELINE.json `configs` (paper config N=256 L=20 B=256 H=512 P=3 X=8 R=4, 8 kHz, synthetic mixtures,
+reference-default random init):
+    --config 0  one 4 s mixture, forward + cal_loss (the reference's CPU-runnable case)
+    --config 1  (default) training step, batch 3 per GPU x 4 s: fwd + PIT SI-SNR + bwd (+ NCCL all-reduce) + clip(5) + Adam
+                — the body of the reference's hot loop (src/solver.py:188-196)
+    --config 2  causal cLN variant, batch 32 x 4 s, forward
+    --config 3  3-speaker (C=3, 6-permutation PIT) training step, batch 16 per GPU x 4 s
+    --config 4  long-utterance inference, 8 x 60 s per GPU (64 x 60 s sharded by utterance over 8 GPUs, no collective)
+`--mode` overrides the config's own mode (e.g. `--config 1 --mode fwd`: forward throughput of the headline batch).
+One JSON line on stdout (rank 0).
 
 `value`  : whole-job audio-s/s with inputs resident in HBM, timed with CUDA events over exactly K steps.
-`e2e`    : the same through the public API with HOST (pinned) inputs: H2D of mixture/source/lengths and a D2H read of
-           the loss inside the timed region, every step.
-`roofline`: the dominant kernel (the 1x1-conv GEMM) timed live on its own launches.
+`e2e`    : the same through the public API with HOST (pinned) inputs: H2D of the step's inputs and a D2H read of its
+           result (the loss; for forward modes a checksum of the estimate) inside the timed region, every step.
+`roofline`: the dominant kernel timed live on its own launches (L2 flushed between them).
 `cpu_baseline`: the CPU oracle port of the reference step on the box's host cores (rank 0, N=1, bounded sample).
 `--impl reference`: times that CPU port alone, same metric/config (the reference has no GPU-specific code and is
            not pip-installable).
 """
 import argparse
+import csv
 import ctypes
 import json
 import os
@@ -32,10 +39,41 @@ import torch  # noqa: E402
 
 PAPER = dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu")
 SR = 8000
-PER_GPU_BATCH = 3
-SEG_SECONDS = 4
-WORKLOAD = ("configs[1]: paper config N=256 L=20 B=256 H=512 P=3 X=8 R=4 C=2 gLN non-causal, batch 3 per GPU x 4 s "
-            "@ 8 kHz, training step = fwd + PIT SI-SNR + bwd (+ NCCL grad all-reduce) + clip(5) + Adam")
+PAPER_STR = "N=256 L=20 B=256 H=512 P=3 X=8 R=4"
+TRAIN_STR = "training step = fwd + PIT SI-SNR + bwd (+ NCCL grad all-reduce) + clip(5) + Adam"
+CONFIGS = {
+    0: dict(model={}, M=1, seconds=4, mode="fwd_loss",
+            workload=f"configs[0]: paper config {PAPER_STR} C=2 gLN non-causal, one 4 s @ 8 kHz mixture, fp32 forward + cal_loss"),
+    1: dict(model={}, M=3, seconds=4, mode="train",
+            workload=f"configs[1]: paper config {PAPER_STR} C=2 gLN non-causal, batch 3 per GPU x 4 s @ 8 kHz, {TRAIN_STR}"),
+    2: dict(model=dict(norm_type="cLN", causal=True), M=32, seconds=4, mode="fwd",
+            workload=f"configs[2]: causal cLN variant (causal=1, norm_type=cLN, Chomp1d) of the paper config {PAPER_STR} C=2, "
+                     "batch 32 per GPU x 4 s @ 8 kHz, forward"),
+    3: dict(model=dict(C=3), M=16, seconds=4, mode="train",
+            workload=f"configs[3]: 3-speaker (C=3, 6-permutation PIT) paper config {PAPER_STR} gLN non-causal, batch 16 per GPU x 4 s "
+                     f"@ 8 kHz, {TRAIN_STR}"),
+    4: dict(model={}, M=8, seconds=60, mode="fwd",
+            workload=f"configs[4]: long-utterance inference, paper config {PAPER_STR} C=2 gLN non-causal, 8 x 60 s @ 8 kHz per GPU "
+                     "(64 x 60 s sharded by utterance over 8 GPUs, no collective; gLN reduction over ~48k frames per utterance)"),
+}
+METRIC = {"train": "audio-seconds separated per second (training step)",
+          "fwd": "audio-seconds separated per second (forward)",
+          "fwd_loss": "audio-seconds separated per second (forward + cal_loss)"}
+
+
+def model_kwargs(cfg_id):
+    kw = dict(PAPER)
+    kw.update(CONFIGS[cfg_id]["model"])
+    return kw
+
+
+def config_dict(cfg_id, mode, world):
+    """The `config` object of the JSON line — identical for the B200 arm and the reference arm."""
+    c = CONFIGS[cfg_id]
+    return {"workload": c["workload"] + ("" if mode == c["mode"] else f" [--mode {mode}]"), "config_id": cfg_id,
+            "mode": mode, "per_gpu_batch": c["M"], "segment_s": c["seconds"], "global_batch": c["M"] * world,
+            "parallelism": f"dp{world}" if mode == "train" else f"utterance-sharded x{world} (no collective)",
+            "l2": "per-step working set exceeds L2 (126 MB); roofline kernel timed with an explicit L2 flush between launches"}
 
 
 def synthetic(M, T, C, L, seed):
@@ -57,6 +95,31 @@ def peaks():
         return p, "measured (MEASURED_PEAKS.json)"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the newest committed `ncu --set full` raw page under
+    profiles/ that holds a kernel whose name contains `kernel_substr`; (None, why) when there is none."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        pages = sorted((f for f in os.listdir(pdir) if f.endswith("_full_raw.csv")), reverse=True)
+    except OSError:
+        return None, "profiles/ is missing"
+    for fn in pages:
+        try:
+            with open(os.path.join(pdir, fn), newline="") as fh:
+                rows = list(csv.reader(fh))
+            hdr, units = rows[0], rows[1]
+            ik = hdr.index("Kernel Name")
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    tot = float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+                    return int(tot), f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/{fn})"
+        except Exception:
+            continue
+    return None, "no ncu --set full capture of this kernel under profiles/"
 
 
 class ClockSampler:
@@ -110,54 +173,72 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def reference_steps(n_steps, warmup, M, T, budget_s=150.0):
-    """The reference training step (solver.py:188-196) restated on the CPU oracle, all host threads.
+def reference_steps(cfg_id, mode, n_steps, warmup, budget_s=150.0):
+    """The reference step of this config restated on the CPU oracle, all host threads.  The sample is bounded: when the
+    probe step says the full per-GPU batch would not finish in `budget_s`, the batch is cut to one utterance (and a 60 s
+    utterance to 8 s) and the throughput is that of the sample — labelled in `sample`.
     Returns (audio_seconds_per_second, seconds_per_step, sample description, cores)."""
     from oracle import conv_tasnet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.Config(**PAPER)
+    kw = model_kwargs(cfg_id)
+    cfg = O.Config(**kw)
     sd = O.init_state_dict(cfg, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    M, T = CONFIGS[cfg_id]["M"], CONFIGS[cfg_id]["seconds"] * SR
+    train = mode == "train"
+    params = {k: v.clone().requires_grad_(train) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3) if train else None
 
     def one(mix, src, lens):
-        est = O.forward(cfg, params, mix)
-        loss, *_ = O.cal_loss(src, est, lens)
-        opt.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(list(params.values()), 5)
-        opt.step()
-        return loss.item()
+        if train:
+            est = O.forward(cfg, params, mix)
+            loss, *_ = O.cal_loss(src, est, lens)
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), 5)
+            opt.step()
+            return loss.item()
+        with torch.no_grad():
+            est = O.forward(cfg, params, mix, training=False)
+            if mode == "fwd_loss":
+                return O.cal_loss(src, est, lens)[0].item()
+            return est.abs().sum().item()
 
-    mix, src, lens = synthetic(M, T, cfg.C, cfg.L, 1234 + 2)
+    # probe on one short utterance to size the sample
+    m_used, t_used = M, T
+    pm, ps, pl = synthetic(1, min(T, 4 * SR), cfg.C, cfg.L, 99)
     t0 = time.perf_counter()
-    one(mix, src, lens)  # first warm-up, also the probe that sizes the sample
-    probe = time.perf_counter() - t0
-    m_used = M
-    if probe * (n_steps + max(0, warmup - 1)) > budget_s and M > 1:
-        m_used = 1  # bounded sample: one utterance of the batch
-        mix, src, lens = mix[:1], src[:1], torch.full((1,), T, dtype=torch.long)
+    one(pm, ps, pl)
+    probe = (time.perf_counter() - t0) / (min(T, 4 * SR) / SR)  # seconds of CPU per audio-second (cold)
+    total_steps = n_steps + max(0, warmup)
+    if probe * M * (T / SR) * total_steps > budget_s:
+        m_used = 1
+        if probe * (T / SR) * total_steps > budget_s:
+            t_used = min(T, 8 * SR)
+    mix, src, lens = synthetic(m_used, t_used, cfg.C, cfg.L, 1234 + cfg_id)
     for _ in range(max(0, warmup - 1)):
         one(mix, src, lens)
     t0 = time.perf_counter()
     for _ in range(n_steps):
         one(mix, src, lens)
     dt = (time.perf_counter() - t0) / n_steps
+    what = {"train": "fwd+PIT+bwd+clip+Adam", "fwd": "forward (no_grad)", "fwd_loss": "forward + cal_loss (no_grad)"}[mode]
     sample = (f"{n_steps} steps of the CPU oracle port (torch {torch.__version__}, {cores} threads) on "
-              f"{m_used} x {T / SR:.0f} s of the {M} x {T / SR:.0f} s per-GPU batch, fwd+PIT+bwd+clip+Adam")
-    return m_used * T / SR / dt, dt, sample, cores
+              f"{m_used} x {t_used / SR:.0f} s of the {M} x {T / SR:.0f} s per-GPU batch, {what}"
+              + ("" if (m_used, t_used) == (M, T) else " — bounded sample, throughput of the sample (BASELINE.md §3)"))
+    return m_used * t_used / SR / dt, dt, sample, cores
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, mode):
     if rank != 0:
         return
-    T = SEG_SECONDS * SR
-    val, dt, sample, cores = reference_steps(args.steps, args.warmup, PER_GPU_BATCH, T)
-    line = {"impl": "reference", "metric": "audio-seconds separated per second (training step)", "value": val,
+    val, dt, sample, cores = reference_steps(args.config, mode, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC[mode], "value": val,
             "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD},
+            "data": "synthetic", "config": config_dict(args.config, mode, args.gpus),
+            "reference_batch": "the CPU arm runs ONE per-GPU batch on rank 0 whatever --gpus says (it has no multi-GPU "
+                               "path): only the N=1 ratio is like for like",
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -171,23 +252,27 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default=None, choices=["train", "fwd", "fwd_loss"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run only warm-up + K device-resident steps (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                     "one captured CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    mode = args.mode or CONFIGS[args.config]["mode"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, mode)
         return
 
     import torch.distributed as dist
     from conv_tasnet_b200 import ConvTasNet, cal_loss, _lib
     from conv_tasnet_b200.data_parallel import ShardedDataParallel
+    from conv_tasnet_b200.graph import GraphedInference, GraphedTrainStep
     from conv_tasnet_b200.optim import FusedAdam
 
     if not torch.cuda.is_available():
@@ -196,29 +281,23 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on STDOUT at VERSION/INFO level; stdout carries exactly one JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("CTN_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # NCCL_DEBUG is left as the caller set it
     L = _lib.lib()
 
-    T = SEG_SECONDS * SR
-    M = PER_GPU_BATCH
+    kw = model_kwargs(args.config)
+    T = CONFIGS[args.config]["seconds"] * SR
+    M = CONFIGS[args.config]["M"]
+    train = mode == "train"
     torch.manual_seed(0)
-    model = ConvTasNet(**PAPER).cuda()
-    model.train()
-    dp = ShardedDataParallel(model) if world > 1 else model
-    opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
-    mix_h, src_h, len_h = synthetic(M, T, PAPER["C"], PAPER["L"], 1234 + 2 + rank)
+    model = ConvTasNet(**kw).cuda()
+    model.train() if train else model.eval()
+    # data parallel training shards the batch and all-reduces gradients; inference shards by utterance with no collective
+    dp = ShardedDataParallel(model) if (world > 1 and train) else model
+    opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0) if train else None
+    mix_h, src_h, len_h = synthetic(M, T, kw["C"], kw["L"], 1234 + args.config + rank)
     mix_h, src_h, len_h = mix_h.pin_memory(), src_h.pin_memory(), len_h.pin_memory()
     mix_d, src_d, len_d = mix_h.to(dev), src_h.to(dev), len_h.to(dev)
-
-    def step(mix, src, lens):
-        est = dp(mix)
-        loss, _, _, _ = cal_loss(src, est, lens)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        return loss
+    use_graph = not args.no_graph and not args.profile_only
 
     def sync_all():
         if world > 1:
@@ -238,23 +317,76 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / 1e3
 
-    # ---- one training step captured as a CUDA graph (conv_tasnet_b200.graph.GraphedTrainStep: the launch sequence is
-    # static — no host sync, no allocation in the C ABI, device-side step counter) and replayed per step ------------
-    from conv_tasnet_b200.graph import GraphedInference, GraphedTrainStep
-    use_graph = not args.no_graph and not args.profile_only
-    gstep = GraphedTrainStep(dp, opt) if use_graph else None
     launches_per_step = 0
-    if gstep is not None:
-        n_before = L.ctn_launch_count()
-        gstep(mix_d, src_d, len_d)  # warm-up + capture
-        launches_per_step = (L.ctn_launch_count() - n_before) // (gstep.warmup + 1)
-        if not gstep.captured:
-            gstep = None
+    graphed = False
+    if train:
+        def eager_step(mix, src, lens):
+            est = dp(mix)
+            loss, _, _, _ = cal_loss(src, est, lens)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
 
-    def run_step():
+        # one training step captured as a CUDA graph (conv_tasnet_b200.graph.GraphedTrainStep: the launch sequence is
+        # static — no host sync, no allocation in the C ABI, device-side step counter) and replayed per step
+        gstep = GraphedTrainStep(dp, opt) if use_graph else None
         if gstep is not None:
-            return gstep(mix_d, src_d, len_d)
-        return step(mix_d, src_d, len_d)
+            n_before = L.ctn_launch_count()
+            gstep(mix_d, src_d, len_d)  # warm-up + capture
+            launches_per_step = (L.ctn_launch_count() - n_before) // (gstep.warmup + 1)
+            if not gstep.captured:
+                gstep = None
+        graphed = gstep is not None
+
+        def run_step():
+            return gstep(mix_d, src_d, len_d) if gstep is not None else eager_step(mix_d, src_d, len_d)
+
+        def e2e_step():  # H2D from pinned memory (into the graph's static inputs), the step, D2H of the loss
+            if gstep is not None:
+                return gstep(mix_h, src_h, len_h).item()
+            return eager_step(mix_h.to(dev, non_blocking=True), src_h.to(dev, non_blocking=True),
+                              len_h.to(dev, non_blocking=True)).item()
+        h2d, d2h = mix_h.numel() * 4 + src_h.numel() * 4 + len_h.numel() * 8, 4
+    else:
+        infer = GraphedInference(model) if use_graph else model
+        with_loss = mode == "fwd_loss"
+
+        def fwd(mix, src, lens):
+            with torch.no_grad():
+                est = infer(mix)
+                if with_loss:
+                    return cal_loss(src, est, lens)[0]
+                return est
+
+        if use_graph:  # kernels per step, counted on one eager pass (the graph replays the same sequence)
+            n_before = L.ctn_launch_count()
+            with torch.no_grad():
+                est0 = model(mix_d)
+                if with_loss:
+                    cal_loss(src_d, est0, len_d)
+            launches_per_step = L.ctn_launch_count() - n_before
+            del est0
+            fwd(mix_d, src_d, len_d)
+            graphed = True
+
+        def run_step():
+            return fwd(mix_d, src_d, len_d)
+
+        if with_loss:
+            def e2e_step():
+                return fwd(mix_h.to(dev, non_blocking=True) if not use_graph else mix_h, src_h.to(dev, non_blocking=True),
+                           len_h.to(dev, non_blocking=True)).item()
+            h2d, d2h = mix_h.numel() * 4 + src_h.numel() * 4 + len_h.numel() * 8, 4
+        else:
+            est_h = torch.empty(M, kw["C"], T, dtype=torch.float32).pin_memory()
+
+            def e2e_step():  # separate.py's use: mixture up, separated sources down
+                est = fwd(mix_h if use_graph else mix_h.to(dev, non_blocking=True), None, None)
+                est_h.copy_(est, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return float(est_h[0, 0, 0])
+            h2d, d2h = mix_h.numel() * 4, est_h.numel() * 4
 
     # ---- device-resident throughput -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -263,7 +395,7 @@ def main():
     sampler.start()
     n0 = L.ctn_launch_count()
     secs = timed(run_step, args.steps)
-    launches = (launches_per_step * args.steps) if gstep is not None else (L.ctn_launch_count() - n0)
+    launches = (launches_per_step * args.steps) if graphed else (L.ctn_launch_count() - n0)
     audio = world * M * T / SR * args.steps
     value = audio / secs
     if args.profile_only:
@@ -273,93 +405,113 @@ def main():
         return
 
     # ---- end to end through the public API with host inputs -------------------------------------------
-    losses = []
-
-    def e2e_step():
-        if gstep is not None:  # H2D from pinned memory into the graph's static inputs, replay, D2H of the loss
-            losses.append(gstep(mix_h, src_h, len_h).item())
-            return
-        mix = mix_h.to(dev, non_blocking=True)
-        src = src_h.to(dev, non_blocking=True)
-        lens = len_h.to(dev, non_blocking=True)
-        losses.append(step(mix, src, lens).item())  # D2H read of the loss, every step
-
+    last = None
     for _ in range(2):
-        e2e_step()
-    secs_e2e = timed(e2e_step, args.steps)
+        last = e2e_step()
+
+    def e2e_timed():
+        nonlocal last
+        last = e2e_step()
+    secs_e2e = timed(e2e_timed, args.steps)
     clocks = sampler.stop()
-    h2d = mix_h.numel() * 4 + src_h.numel() * 4 + len_h.numel() * 8
 
-    # ---- forward-only throughput (the metric's other half) --------------------------------------------
-    model.eval()
-    with torch.no_grad():
-        infer = GraphedInference(dp) if use_graph else dp
-        for _ in range(3):
-            infer(mix_d)
-        secs_fwd = timed(lambda: infer(mix_d), args.steps)
-    model.train()
+    # ---- the metric's other half for the training configs: forward-only throughput of the same batch ---
+    fwd_line = None
+    if train:
+        model.eval()
+        with torch.no_grad():
+            inf = GraphedInference(model) if use_graph else model
+            for _ in range(3):
+                inf(mix_d)
+            secs_fwd = timed(lambda: inf(mix_d), args.steps)
+        model.train()
+        fwd_line = {"value": audio / secs_fwd, "unit": "audio-s/s", "ms_per_step": secs_fwd / args.steps * 1e3}
 
-    # ---- roofline of the dominant kernel by time share (profiles/r1_final_summary.md): the weight-gradient GEMM
-    # dW[H,B] = dz1[F,H]^T x[F,B] on tcgen05 (bf16x3 split, MN-major operands), timed live on its own launches --------
+    # ---- roofline of the dominant kernel, timed live on its own launches with the L2 flushed in between ----------
     pk, pk_src = peaks()
     K = L.ctn_num_frames(ctypes.byref(model._cfg), T)
     F = M * K
-    Gm = torch.randn(F, PAPER["H"], device=dev)
-    Xm = torch.randn(F, PAPER["B"], device=dev)
-    dWm = torch.zeros(PAPER["H"], PAPER["B"], device=dev)
+    Bc, Hc = kw["B"], kw["H"]
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)  # >> L2 (126 MB); also keeps the GPU busy while the
     # host enqueues the timed launch, so the event pair brackets the kernel alone and not host launch latency
     st = _lib.stream()
+    if train:  # weight gradient dW[H,B] = dz1[F,H]^T x[F,B] (2 per TemporalBlock + 2), the largest kernel of the step
+        Gm = torch.randn(F, Hc, device=dev)
+        Xm = torch.randn(F, Bc, device=dev)
+        dWm = torch.zeros(Hc, Bc, device=dev)
 
-    def wgrad():
-        _lib.check(L.ctn_wgrad(Gm.data_ptr(), Xm.data_ptr(), dWm.data_ptr(), F, PAPER["H"], PAPER["B"], K, None, None,
-                               None, None, None, st))
+        def kern():
+            _lib.check(L.ctn_wgrad(Gm.data_ptr(), Xm.data_ptr(), dWm.data_ptr(), F, Hc, Bc, K, None, None, None, None,
+                                   None, st))
+        kname, ksub = ("tc_wgrad_kernel<256>: dW[512,256] = dz1[F,512]^T x[F,256] (tcgen05, bf16x3 split, MN-major "
+                       "operands, split-K + coalesced red.v4)"), "tc_wgrad_kernel"
+        n_launch = 2 * kw["R"] * kw["X"] + 2
+    else:      # the 1x1 bottleneck conv of every TemporalBlock: z1[F,H] = x[F,B] W1^T with the gLN sums in the epilogue
+        Am = torch.randn(F, Bc, device=dev)
+        Wm = torch.randn(Hc, Bc, device=dev) / 16
+        hi = Wm.to(torch.bfloat16)  # pre-split bf16 hi/lo planes, as the model holds them for inference
+        lo = (Wm - hi.float()).to(torch.bfloat16)
+        Dm = torch.empty(F, Hc, device=dev)
+
+        def kern():
+            _lib.check(L.ctn_conv1x1_planes(Am.data_ptr(), hi.data_ptr(), lo.data_ptr(), 0, Dm.data_ptr(), F, Hc, Bc, K,
+                                            st))
+        kname, ksub = ("1x1-conv GEMM z1[F,512] = x[F,256] W1^T (tcgen05, bf16x3 split of the inference forward, "
+                       "pre-split weight planes)"), "gemm_kernel"
+        n_launch = 2 * kw["R"] * kw["X"] + 2
     for _ in range(3):
-        wgrad()
+        kern()
     reps, tot = 10, 0.0
     for _ in range(reps):
         flush.zero_()  # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        wgrad()
+        kern()
         e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1) * 1e-3
     t_k = tot / reps
-    flops = 2.0 * F * PAPER["B"] * PAPER["H"]
+    flops = 2.0 * F * Bc * Hc
     ach = flops / t_k / 1e12
-    roofline = {"kernel": "tc_wgrad_kernel<256>: dW[512,256] = dz1[F,512]^T x[F,256] (tcgen05, bf16x3 split, MN-major "
-                "operands, split-K + coalesced red.v4), the largest single kernel of the step (2 per TemporalBlock + 2)", "bound": "tensor", "achieved": ach,
-                "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                "traffic": 30042112, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per "
-                "launch (profiles/r1b_wgrad_full_raw.csv); algorithmic input 29.5 MB",
+    traffic, traffic_src = profiled_traffic(ksub)
+    roofline = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk_src + ", bf16 burst (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the "
                 "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops,
-                "launches_per_step": 2 * PAPER["R"] * PAPER["X"] + 2,
-                "share_of_step": (2 * PAPER["R"] * PAPER["X"] + 2) * t_k / (secs / args.steps)}
+                "alg_bytes_per_launch": 4.0 * F * (Bc + Hc), "launches_per_step": n_launch,
+                "share_of_step": n_launch * t_k / (secs / args.steps)}
 
     # whole-step algorithmic rates (SURVEY §8d per-frame figures x frames)
     frames = world * F
-    step_flops = frames * (17.30e6 * 3 - 2 * PAPER["N"] * PAPER["L"])
-    step_bytes = frames * (91422 + 241950 + 5 * PAPER["C"] * 10) * 4 + 10 * 4 * 8710720 * world
+    N_, L_, C_, RX = kw["N"], kw["L"], kw["C"], kw["R"] * kw["X"]
+    S_ = L_ // 2
+    n_params = 8710720 + (C_ - 2) * N_ * Bc
+    mac_fwd = N_ * L_ + N_ * Bc + RX * (Bc * Hc + Hc * kw["P"] + Hc * Bc) + Bc * C_ * N_ + C_ * N_ * L_
+    e_fwd = S_ + 3 * N_ + 2 * Bc + C_ * S_ + RX * (3 * Bc + 4 * Hc)
+    e_bwd = S_ + C_ * S_ + 5 * Bc + 8 * N_ + 2 * C_ * N_ + RX * (5 * Bc + 12 * Hc)
+    if train:
+        step_flops = frames * (2 * mac_fwd * 3 - 2 * N_ * L_)
+        step_bytes = frames * (e_fwd + e_bwd + 5 * C_ * S_) * 4 + 10 * 4 * n_params * world
+    else:
+        step_flops = frames * 2 * mac_fwd
+        step_bytes = frames * (e_fwd + (2 * C_ * S_ if mode == "fwd_loss" else 0)) * 4 + 4 * n_params * world
     t_step = secs / args.steps
 
-    line = {"metric": "audio-seconds separated per second (training step)", "value": value, "unit": "audio-s/s",
+    line = {"metric": METRIC[mode], "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": M, "segment_s": SEG_SECONDS, "global_batch": M * world,
-                       "parallelism": f"dp{world}", "l2": "per-step working set (1.7 GB activation stash) exceeds L2 "
-                       "(126 MB); roofline kernel timed with an explicit 1 GB L2 flush between launches"},
-            "e2e": {"value": audio / secs_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": secs_e2e / args.steps * 1e3, "last_loss": losses[-1]},
-            "fwd": {"value": audio / secs_fwd, "unit": "audio-s/s", "ms_per_step": secs_fwd / args.steps * 1e3},
-            "gpu_launches": int(launches), "cuda_graph": gstep is not None, "clocks": clocks, "roofline": roofline,
+            "config": config_dict(args.config, mode, world),
+            "e2e": {"value": audio / secs_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": secs_e2e / args.steps * 1e3, "last_result": last},
+            "gpu_launches": int(launches), "cuda_graph": graphed, "clocks": clocks, "roofline": roofline,
             "step_algorithmic": {"tflops": step_flops / t_step / 1e12, "gbs": step_bytes / t_step / 1e9,
                                  "hbm_bound_ms": step_bytes / world / (pk["hbm_gbs"] * 1e9) * 1e3,
                                  "frac_of_hbm_bound": (step_bytes / world / (pk["hbm_gbs"] * 1e9)) / t_step}}
+    if fwd_line is not None:
+        line["fwd"] = fwd_line
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, dt, sample, cores = reference_steps(2, 1, M, T, budget_s=30.0)
+        val, dt, sample, cores = reference_steps(args.config, mode, 2, 1, budget_s=30.0)
         line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
     if world > 1:
         dist.barrier()

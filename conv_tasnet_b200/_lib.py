@@ -40,6 +40,8 @@ SIGNATURES = {
     "ctn_pit_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "ctn_pit_forward": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ctn_pit_backward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_sisnri_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "ctn_sisnri": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ctn_reorder_source": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "ctn_overlap_and_add": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ctn_clip_grad_norm": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
@@ -49,6 +51,7 @@ SIGNATURES = {
     "ctn_row_stats": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "ctn_conv1x1": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                             c_vp, c_vp, c_vp]),
+    "ctn_conv1x1_planes": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     "ctn_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ctn_prep_normfold": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ctn_dwconv_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,

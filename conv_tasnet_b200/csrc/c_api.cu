@@ -26,6 +26,9 @@ int run_pit_forward(const float*, float*, const int64_t*, int, int, int, float*,
 int run_pit_backward(const float*, const float*, const int64_t*, const float*, const float*, int, int, int, float*,
                      cudaStream_t);
 int run_reorder(const float*, const int64_t*, int, int, int64_t, float*, cudaStream_t);
+int64_t sisnri_workspace_bytes(int, int);
+int run_sisnri(const float*, const float*, const float*, const int64_t*, int, int, int, float*, float*, void*,
+               cudaStream_t);
 int run_clip_grad_norm(float*, int64_t, float, float*, void*, cudaStream_t);
 int run_adam_step(float*, const float*, float*, float*, int64_t, float, float, float, float, float, int64_t*,
                   cudaStream_t);
@@ -54,6 +57,14 @@ using namespace ctn;
 extern "C" {
 
 int64_t ctn_pit_workspace_bytes(int32_t B, int32_t C) { return pit_workspace_bytes(B, C); }
+
+int64_t ctn_sisnri_workspace_bytes(int32_t B, int32_t C) { return sisnri_workspace_bytes(B, C); }
+
+int32_t ctn_sisnri(const float* source, const float* reordered_est, const float* mixture, const int64_t* lengths, int32_t B,
+                   int32_t C, int32_t T, float* sisnri, float* sisnr_est, void* ws, cudaStream_t stream) {
+  CTN_REQUIRE(source && reordered_est && mixture && lengths && sisnri && ws, "sisnri: null pointer");
+  return run_sisnri(source, reordered_est, mixture, lengths, B, C, T, sisnri, sisnr_est, ws, stream);
+}
 
 int32_t ctn_assemble_batch(const float* packed_mix, const float* packed_src, const int64_t* offsets, int32_t B, int32_t C,
                            int32_t T, float* padded_mixture, float* padded_source, int64_t* lengths,
@@ -129,6 +140,16 @@ int32_t ctn_conv1x1(const float* A, const float* W, int32_t w_is_kn, float* D, i
   a.res = res; a.stat_out = stat_out; a.alpha_out = alpha_out;
   CTN_REQUIRE((c1 == nullptr) == (c2 == nullptr), "conv1x1: c1 and c2 go together");
   CTN_REQUIRE(c1 == nullptr || gln_acc != nullptr || rowstat != nullptr, "conv1x1: norm fold needs statistics");
+  return launch_gemm(a, stream);
+}
+
+int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t tf32, float* D, int64_t F, int32_t O,
+                           int32_t Kd, int32_t K, cudaStream_t stream) {
+  CTN_REQUIRE(A && W_hi && W_lo && D, "conv1x1_planes: null pointer");
+  CTN_REQUIRE(Kd % 64 == 0 && O % 16 == 0, "conv1x1_planes: needs Kd %% 64 == 0 and O %% 16 == 0 (got Kd=%d O=%d)", Kd, O);
+  GemmArgs a = {};
+  a.A = A; a.D = D; a.F = F; a.O = O; a.Kd = Kd; a.K = K;
+  a.W_hi = W_hi; a.W_lo = W_lo; a.tf32 = tf32 ? 1 : 0;
   return launch_gemm(a, stream);
 }
 

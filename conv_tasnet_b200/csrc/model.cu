@@ -102,6 +102,8 @@ int run_bn_bwd_apply(float*, const float*, const float*, const float*, const flo
 
 bool tc_gemm_eligible(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
+bool ts_gemm_eligible(const GemmArgs& a);
+int launch_gemm_ts(const GemmArgs& a, cudaStream_t s);  // -1: epilogue combination not built (fall back)
 bool tc_wgrad_eligible(const WgradArgs& a);
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t s);
 int run_split_planes(const float*, int, int, int, int64_t, void*, void*, int64_t, int, cudaStream_t);
@@ -137,7 +139,10 @@ static bool env_flag(const char* name) {
   return e != nullptr && e[0] == '1';
 }
 int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
-  if (force_simt() || a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) return launch_gemm_simt(a0, s);
+  // frame-major kernel (gemm_ts.cu): any O % 16 == 0; channel-major kernel (gemm_tc.cu, CTN_GEMM_SS=1): O % 128 == 0
+  static const bool use_ss = env_flag("CTN_GEMM_SS");
+  const bool off_grid = use_ss ? (a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) : (a0.Kd % 64 != 0 || a0.O % 16 != 0);
+  if (force_simt() || off_grid) return launch_gemm_simt(a0, s);
   static const bool simt_fwd = env_flag("CTN_SIMT_FWD"), simt_bwd = env_flag("CTN_SIMT_BWD");  // A/B debugging only
   if ((simt_fwd && !a0.w_is_kn) || (simt_bwd && a0.w_is_kn)) return launch_gemm_simt(a0, s);
   GemmArgs a = a0;
@@ -153,6 +158,13 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
     else
       CTN_TRY(run_split_planes_tf32(a.W, (int64_t)a.O * a.Kd, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo),
                                     0, s));
+  }
+  // CTN_TS_MASK (debug): which flavours take the frame-major kernel: 1 = tf32 without fold, 2 = tf32 with fold, 4 = bf16
+  static const int ts_mask = getenv("CTN_TS_MASK") ? atoi(getenv("CTN_TS_MASK")) : 7;
+  const int flavour = a.tf32 ? (a.c1 != nullptr ? 2 : 1) : 4;
+  if (!use_ss && (ts_mask & flavour) && ts_gemm_eligible(a)) {
+    const int rc = launch_gemm_ts(a, s);
+    if (rc >= 0) return rc;
   }
   if (!tc_gemm_eligible(a)) return launch_gemm_simt(a0, s);
   return launch_gemm_tc(a, s);

@@ -3,11 +3,26 @@
 The C ABI launches a static sequence of kernels (no host sync, no allocation, device-side Adam step counter), so one
 training step — forward, PIT loss, backward, gradient all-reduce, clip, Adam — is captured once per input shape and
 replayed with a single graph launch; inputs are copied into the graph's static buffers (that copy is the H2D transfer
-when the caller hands over pinned host tensors)."""
+when the caller hands over pinned host tensors).
+
+Each captured shape owns its workspace (the model's grow-only cache may replace its buffer at any time; a graph holds raw
+pointers), the warm-up before a capture leaves no trace (parameters, Adam state and BatchNorm statistics are restored),
+and a change of the optimizer's hyper-parameters (src/solver.py:169-176 halves the learning rate through
+`optimizer.load_state_dict`) triggers a re-capture, since the kernels take them by value."""
+import collections
+import warnings
+
 import torch
 
 from . import _lib
 from .pit_criterion import _pit_forward_raw, cal_loss
+
+
+class _Captured:
+    """one input shape: static input buffers, the workspace the graphs point into, the graphs, the loss tensor"""
+
+    def __init__(self):
+        self.static = self.ws = self.graph = self.graph2 = self.stage_graphs = self.keep = self.loss = self.hyper = None
 
 
 class GraphedTrainStep:
@@ -17,12 +32,13 @@ class GraphedTrainStep:
     (ShardedDataParallel) the collectives stay outside the graphs and overlap them: graph 0 = forward + PIT loss + its
     gradient + backward stage 0, graphs 1..R+1 = the remaining backward stages; after each replay the finished slice of
     the flat gradient buffer is all-reduced asynchronously on NCCL's stream while the next graph runs; the last graph
-    (clip + Adam) waits for the collectives.  Falls back to eager launches if capture is refused."""
+    (clip + Adam) waits for the collectives.  If capture is refused the step runs eagerly and a warning says why
+    (`strict=True` raises instead).  Up to `max_shapes` input shapes stay captured (least recently used evicted)."""
 
-    def __init__(self, model, optimizer, warmup=3):
+    def __init__(self, model, optimizer, warmup=3, max_shapes=2, strict=False):
         self.model, self.optimizer, self.warmup = model, optimizer, warmup
-        self._shape, self._graph, self._graph2, self._static, self._loss = None, None, None, None, None
-        self._stage_graphs, self._keep = None, None
+        self.max_shapes, self.strict = max_shapes, strict
+        self._cap = collections.OrderedDict()  # shape key -> _Captured (graph is None: capture refused, run eagerly)
         self.captured = False
 
     def _fwd_bwd(self, mix, src, lens):
@@ -40,39 +56,79 @@ class GraphedTrainStep:
     def _dp(self):
         return self.model if getattr(self.model, "_enabled", False) and hasattr(self.model, "all_reduce_flat") else None
 
+    def _module(self):
+        return getattr(self.model, "module", self.model)
+
+    def _snapshot(self):
+        m, o = self._module(), self.optimizer
+        snap = [m.flat_params.clone()]
+        for name in ("exp_avg", "exp_avg_sq", "step_count", "grad_norm"):
+            if hasattr(o, name):
+                snap.append(getattr(o, name).clone())
+        if getattr(m, "_bn_state", None) is not None:
+            snap += [m._bn_state.clone(), m._bn_count.clone()]
+        return snap
+
+    def _restore(self, snap):
+        m, o = self._module(), self.optimizer
+        it = iter(snap)
+        m.flat_params.copy_(next(it))
+        for name in ("exp_avg", "exp_avg_sq", "step_count", "grad_norm"):
+            if hasattr(o, name):
+                getattr(o, name).copy_(next(it))
+        if getattr(m, "_bn_state", None) is not None:
+            m._bn_state.copy_(next(it))
+            m._bn_count.copy_(next(it))
+
+    def _hyper(self):
+        return self.optimizer.hyper() if hasattr(self.optimizer, "hyper") else None
+
     def _capture(self, mix, src, lens):
         dev = mix.device
-        self._static = (torch.empty_like(mix, device=dev), torch.empty_like(src, device=dev),
-                        torch.empty_like(lens, device=dev))
-        for d, s in zip(self._static, (mix, src, lens)):
+        m = self._module()
+        c = _Captured()
+        c.static = (torch.empty_like(mix, device=dev), torch.empty_like(src, device=dev),
+                    torch.empty_like(lens, device=dev))
+        for d, s in zip(c.static, (mix, src, lens)):
             d.copy_(s)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(self.warmup):
-                self._eager(*self._static)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        dp = self._dp()
+        c.ws = torch.empty(m.workspace_bytes(mix.shape[0], mix.shape[1], True), dtype=torch.uint8, device=dev)
+        c.hyper = self._hyper()
+        m._ws_override = c.ws
         try:
-            if dp is None:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._loss = self._eager(*self._static)
-                self._graph, self._graph2 = g, None
-            else:  # collectives stay eager, between the per-stage graphs
-                self._capture_staged(dp)
-            self.captured = True
-        except Exception:  # capture refused: keep working, eagerly
+            if self.warmup > 0:  # side-effect free: the state the warm-up steps changed is put back
+                snap = self._snapshot()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(self.warmup):
+                        self._eager(*c.static)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                self._restore(snap)
             torch.cuda.synchronize(dev)
-            self._graph, self._graph2, self._stage_graphs, self.captured = None, None, None, False
-        self._shape = (tuple(mix.shape), tuple(src.shape))
+            dp = self._dp()
+            try:
+                if dp is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        c.loss = self._eager(*c.static)
+                    c.graph = g
+                else:  # collectives stay eager, between the per-stage graphs
+                    self._capture_staged(dp, c)
+            except Exception as e:  # capture refused: keep working, eagerly — but say so
+                torch.cuda.synchronize(dev)
+                c.graph = c.graph2 = c.stage_graphs = None
+                if self.strict:
+                    raise
+                warnings.warn(f"GraphedTrainStep: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+        finally:
+            m._ws_override = None
+        return c
 
-    def _capture_staged(self, dp):
+    def _capture_staged(self, dp, c):
         """forward + loss + backward as R+2 graphs cut at the gradient-bucket boundaries (driving the C ABI directly:
         ctn_model_forward, ctn_pit_forward/backward, ctn_model_backward_stage), then the optimizer graph"""
         m = dp.module
-        mix, src, lens = self._static
+        mix, src, lens = c.static
         lens = lens.to(torch.int64)
         L = _lib.lib()
         pool = torch.cuda.graph_pool_handle()
@@ -99,59 +155,83 @@ class GraphedTrainStep:
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, pool=pool):
             self.optimizer.step()
-        self._keep = (est, ws, token, coef, d_est, one, lens)  # tensors the graphs reference
-        self._loss = loss.view(())
-        self._graph, self._graph2, self._stage_graphs = graphs[0], g2, graphs
+        c.keep = (est, ws, token, coef, d_est, one, lens)  # tensors the graphs reference
+        c.loss = loss.view(())
+        c.graph, c.graph2, c.stage_graphs = graphs[0], g2, graphs
 
     def __call__(self, mixture, source, lengths):
-        if self._shape != (tuple(mixture.shape), tuple(source.shape)):
-            self._capture(mixture.to(self._device_of(), non_blocking=True), source.to(self._device_of(), non_blocking=True),
-                          torch.as_tensor(lengths).to(device=self._device_of(), dtype=torch.int64, non_blocking=True))
-        if self._graph is None:
-            dev = self._device_of()
+        dev = self._device_of()
+        key = (tuple(mixture.shape), tuple(source.shape))
+        c = self._cap.get(key)
+        if c is not None and c.hyper != self._hyper():  # lr / betas / clip norm are baked into the captured kernels
+            del self._cap[key]
+            c = None
+        if c is None:
+            while len(self._cap) >= max(1, self.max_shapes):
+                self._cap.popitem(last=False)
+            c = self._capture(mixture.to(dev, non_blocking=True), source.to(dev, non_blocking=True),
+                              torch.as_tensor(lengths).to(device=dev, dtype=torch.int64, non_blocking=True))
+            self._cap[key] = c
+        else:
+            self._cap.move_to_end(key)
+        self.captured = c.graph is not None
+        if c.graph is None:
             return self._eager(mixture.to(dev, non_blocking=True), source.to(dev, non_blocking=True),
                                torch.as_tensor(lengths).to(dev, non_blocking=True))
-        for d, s in zip(self._static, (mixture, source, lengths)):
+        for d, s in zip(c.static, (mixture, source, lengths)):
             if d.data_ptr() != (s.data_ptr() if isinstance(s, torch.Tensor) and s.is_cuda else -1):
                 d.copy_(torch.as_tensor(s), non_blocking=True)
-        if self._graph2 is None:
-            self._graph.replay()
+        if c.graph2 is None:
+            c.graph.replay()
         else:
             dp = self._dp()
-            for stage, g in enumerate(self._stage_graphs):
+            for stage, g in enumerate(c.stage_graphs):
                 g.replay()
                 dp._on_stage(dp.module, stage)  # async all-reduce of the slice this stage finished
             dp._on_stage(dp.module, -1)         # the current stream waits for the collectives
-            self._graph2.replay()
-        return self._loss
+            c.graph2.replay()
+        return c.loss
 
     def _device_of(self):
-        m = getattr(self.model, "module", self.model)
-        return m.flat_params.device
+        return self._module().flat_params.device
 
 
 class GraphedInference:
-    """infer = GraphedInference(model); est = infer(mixture)   (est is a static buffer, overwritten by the next call)"""
+    """infer = GraphedInference(model); est = infer(mixture)   (est is a static buffer, overwritten by the next call)
 
-    def __init__(self, model):
-        self.model = model
-        self._shape, self._graph, self._in, self._out = None, None, None, None
+    One captured graph (with its own workspace) per input shape, up to `max_shapes` (least recently used evicted)."""
+
+    def __init__(self, model, max_shapes=4):
+        self.model, self.max_shapes = model, max_shapes
+        self._cap = collections.OrderedDict()  # shape -> (graph, static input, static output, workspace)
 
     def __call__(self, mixture):
-        if self._shape != tuple(mixture.shape):
+        key = tuple(mixture.shape)
+        entry = self._cap.get(key)
+        if entry is None:
+            while len(self._cap) >= max(1, self.max_shapes):
+                self._cap.popitem(last=False)
             m = getattr(self.model, "module", self.model)
             dev = m.flat_params.device
-            self._in = torch.empty(mixture.shape, dtype=torch.float32, device=dev)
-            self._in.copy_(mixture)
-            with torch.no_grad():
-                for _ in range(2):
-                    self.model(self._in)
-                torch.cuda.synchronize(dev)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._out = self.model(self._in)
-            self._graph, self._shape = g, tuple(mixture.shape)
-        if self._in.data_ptr() != (mixture.data_ptr() if mixture.is_cuda else -1):
-            self._in.copy_(mixture, non_blocking=True)
-        self._graph.replay()
-        return self._out
+            x = torch.empty(mixture.shape, dtype=torch.float32, device=dev)
+            x.copy_(mixture)
+            ws = torch.empty(m.workspace_bytes(mixture.shape[0], mixture.shape[1], False), dtype=torch.uint8, device=dev)
+            m._ws_override = ws
+            try:
+                with torch.no_grad():
+                    for _ in range(2):
+                        self.model(x)
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = self.model(x)
+            finally:
+                m._ws_override = None
+            entry = self._cap[key] = (g, x, out, ws)
+        else:
+            self._cap.move_to_end(key)
+        g, x, out, _ = entry
+        if x.data_ptr() != (mixture.data_ptr() if mixture.is_cuda else -1):
+            x.copy_(mixture, non_blocking=True)
+        g.replay()
+        return out

@@ -111,6 +111,16 @@ int32_t ctn_pit_backward(const float* source, const float* est_masked, const int
 int32_t ctn_reorder_source(const float* source, const int64_t* idx, int32_t B, int32_t C, int64_t inner,
                            float* out, cudaStream_t stream);
 
+/* cal_SISNRi / cal_SISNR (src/evaluate.py:94-130) on the padded evaluation batch, in one pass on the device:
+ *   source [B,C,T], reordered_est [B,C,T] (cal_loss's reorder_estimate_source), mixture [B,T], lengths [B]
+ *   -> sisnri [B] = mean_c( SI-SNR(source_c, est_c) - SI-SNR(source_c, mixture) ) over t < lengths[b]
+ *   (the reference hard-codes C = 2, src/evaluate.py:103-110; this is the same average for any C).
+ *   sisnr_est [B,C] (optional, may be NULL): cal_SISNR(source_c, est_c) itself (src/evaluate.py:114-130).
+ *   ws: ctn_sisnri_workspace_bytes(B,C) bytes of scratch. */
+int64_t ctn_sisnri_workspace_bytes(int32_t B, int32_t C);
+int32_t ctn_sisnri(const float* source, const float* reordered_est, const float* mixture, const int64_t* lengths,
+                   int32_t B, int32_t C, int32_t T, float* sisnri, float* sisnr_est, void* ws, cudaStream_t stream);
+
 /* utils.overlap_and_add (src/utils.py:9-47): signal [outer, frames, frame_length] -> [outer, out_len] */
 int32_t ctn_overlap_and_add(const float* signal, int64_t outer, int32_t frames, int32_t frame_length,
                             int32_t frame_step, float* out, cudaStream_t stream);
@@ -160,6 +170,13 @@ int32_t ctn_conv1x1(const float* A, const float* W, int32_t w_is_kn, float* D, i
                     int32_t Kd, int32_t K, const float* alpha_in, const float* c1, const float* c2,
                     const double* gln_acc, const float* rowstat, const float* res, double* stat_out,
                     const float* alpha_out, cudaStream_t stream);
+/* The same 1x1 convolution with the weight operand already split into the planes the tensor-core kernels read
+ * ([O, Kd] row-major; tf32 = 1: fp32 planes hi = tf32(W), lo = W - hi; tf32 = 0: bf16 planes hi = bf16(W), lo = bf16(W - hi)),
+ * as the whole-model path holds them (one split per step instead of one per call).  No prologue / epilogue.
+ * Replaces nn.Conv1d(kernel_size=1, bias=False) calls, src/conv_tasnet.py:223,262,191. */
+int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t tf32, float* D, int64_t F,
+                           int32_t O, int32_t Kd, int32_t K, cudaStream_t stream);
+
 /* weight gradient: dW[O,I] += sum_f G[f,o] * act(f,i), act = Act or gamma*(prelu(Act,alpha)-mu)*r+beta when
  * gamma != NULL (stats as above, count = K*I) */
 int32_t ctn_wgrad(const float* G, const float* Act, float* dW, int64_t F, int32_t O, int32_t I, int32_t K,

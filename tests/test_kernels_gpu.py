@@ -331,3 +331,56 @@ def test_clip_and_adam_match_torch():
         call("ctn_adam_step", P(p), P(gc), P(m), P(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, P(step))
         assert rel_err(p.cpu(), pt.detach().cpu()) < 1e-6
     assert step.item() == 3
+
+
+def test_sisnri_kernel_matches_reference_goldens():
+    """ctn_sisnri (csrc/sisnri.cu) through conv_tasnet_b200.evaluate against tests/golden/eval.npz — the reference's own
+    cal_SISNRi / cal_SISNR (src/evaluate.py:94-130) run per utterance after remove_pad — and against the fp64 oracle.
+    Tolerance in dB: 1e-3 against the reference (which computes in float32 numpy), 1e-4 against the fp64 oracle."""
+    from conv_tasnet_b200.evaluate import cal_SISNR, cal_SISNRi, cal_SISNRi_batch
+    z = load_golden("eval.npz")
+    for i in range(int(z["n_cases"])):
+        src, est, mix = (torch.from_numpy(z[f"c{i}_{k}"]).to(dev()) for k in ("src", "est", "mix"))
+        lens = torch.from_numpy(z[f"c{i}_lengths"])
+        got = cal_SISNRi_batch(src, est, mix, lens).cpu().double()
+        assert (got - torch.from_numpy(z[f"c{i}_sisnri"])).abs().max().item() < 1e-3
+        for b, n in enumerate(lens.tolist()):
+            want = O.cal_SISNRi_np(z[f"c{i}_src"][b, :, :n].astype(np.float64), z[f"c{i}_est"][b, :, :n].astype(np.float64),
+                                   z[f"c{i}_mix"][b, :n].astype(np.float64))
+            assert abs(got[b].item() - want) < 1e-4
+        # the single-utterance entry points of the reference API
+        n = int(lens[0])
+        one = cal_SISNRi(src[0, :, :n], est[0, :, :n], mix[0, :n]).item()
+        assert abs(one - z[f"c{i}_sisnri"][0]) < 1e-3
+        s = cal_SISNR(src[0, 1, :n], est[0, 1, :n]).item()
+        assert abs(s - z[f"c{i}_sisnr"][0, 1]) < 1e-3
+
+
+def test_sisnri_kernel_three_speakers_and_empty_tail():
+    """C = 3 (the reference hard-codes two speakers; the kernel averages over any C) and an utterance one sample long."""
+    from conv_tasnet_b200.evaluate import cal_SISNRi_batch
+    g = torch.Generator().manual_seed(21)
+    B, C, T = 3, 3, 5000
+    src = torch.randn(B, C, T, generator=g) * 0.05
+    lens = torch.tensor([5000, 4099, 2])
+    for b, n in enumerate(lens.tolist()):
+        src[b, :, n:] = 0
+    mix = src.sum(1)
+    est = src + 0.01 * torch.randn(B, C, T, generator=g)
+    got = cal_SISNRi_batch(src.to(dev()), est.to(dev()), mix.to(dev()), lens).cpu()
+    for b, n in enumerate(lens.tolist()):
+        s, e, m = (x[b, ..., :n].double().numpy() for x in (src, est, mix))
+        want = np.mean([O.cal_SISNR_np(s[c], e[c]) - O.cal_SISNR_np(s[c], m) for c in range(C)])
+        assert abs(got[b].item() - want) < 1e-3, (b, got[b].item(), want)
+
+
+def test_get_mask_matches_reference():
+    """get_mask (src/pit_criterion.py:102-114) built on the device: ones up to each length, zeros after, [B,1,T]."""
+    from conv_tasnet_b200.pit_criterion import get_mask
+    src = torch.zeros(4, 2, 37, device=dev())
+    lens = torch.tensor([37, 1, 0, 20])
+    got = get_mask(src, lens)
+    want = O.get_mask(src.cpu(), lens)
+    assert got.shape == (4, 1, 37) and got.dtype == src.dtype
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(get_mask(src, lens.to(dev())).cpu(), want)  # lengths already on the device

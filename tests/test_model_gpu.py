@@ -365,3 +365,157 @@ def test_fused_adam_and_graphed_step_match_torch_adam_eager(name):
     with torch.no_grad():
         want = model(mix)
     assert torch.equal(infer(mix), want) and torch.equal(infer(mix.clone()), want)
+
+
+def test_workspace_memory_stays_bounded_over_many_input_lengths():
+    """The reference's loops feed variable-length batches (src/solver.py:183-188 cross-validation with grad enabled,
+    src/evaluate.py:44, src/separate.py:44): the drop-in keeps ONE grow-only workspace per mode, so device memory does
+    not grow with the number of distinct shapes seen."""
+    from conv_tasnet_b200 import cal_loss
+    cfgd, sd, z = golden_model("gln")
+    model = build(cfgd, sd).train()
+    L = cfgd["L"]
+    g = torch.Generator().manual_seed(0)
+
+    def run(T, grad):
+        mix = (torch.randn(2, T, generator=g) * 0.05).cuda()
+        if not grad:
+            with torch.no_grad():
+                return model(mix)
+        src = torch.stack([mix, -mix], dim=1) * 0.5
+        est = model(mix)
+        loss, *_ = cal_loss(src, est, torch.tensor([T, T - 3]))
+        loss.backward()
+        return None
+
+    longest = 6000
+    run(longest, True)
+    run(longest, False)
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    for i in range(40):  # 40 distinct shapes, all shorter than the first
+        T = longest - 37 * (i + 1)
+        run(T, True)
+        run(T - L, False)
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_allocated() <= base + (4 << 20), (base, torch.cuda.memory_allocated())
+    assert len(model._ws_cache) <= 2
+
+
+def test_fused_adam_state_dict_is_interchangeable_with_torch_adam():
+    """`optim_dict` of a checkpoint package (src/conv_tasnet.py:89, src/solver.py:62,126-129): FusedAdam writes and reads
+    torch.optim.Adam's format, in both directions, and resuming from it continues the same trajectory."""
+    from conv_tasnet_b200 import cal_loss
+    from conv_tasnet_b200.optim import FusedAdam
+    cfgd, sd, z = golden_model("gln")
+    mix, src = torch.from_numpy(z["mixture"]).cuda(), torch.from_numpy(z["source"]).cuda()
+    lens = torch.from_numpy(z["lengths"]).cuda()
+
+    def steps(model, opt, n, clip):
+        for _ in range(n):
+            est = model(mix)
+            loss, *_ = cal_loss(src, est, lens)
+            opt.zero_grad()
+            loss.backward()
+            if clip:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+            opt.step()
+
+    # torch.optim.Adam -> FusedAdam
+    a = build(cfgd, sd).train()
+    opt_a = torch.optim.Adam(a.parameters(), lr=2e-3)
+    steps(a, opt_a, 2, True)
+    b = build(cfgd, a.state_dict()).train()
+    opt_b = FusedAdam(b, lr=1e-3, max_grad_norm=5.0)
+    opt_b.load_state_dict(opt_a.state_dict())
+    assert opt_b.lr == 2e-3 and int(opt_b.step_count.item()) == 2
+    steps(a, opt_a, 2, True)
+    steps(b, opt_b, 2, False)
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel_err(q.detach().cpu(), p.detach().cpu()) < 2e-3, k
+    # FusedAdam -> torch.optim.Adam
+    sd_b = opt_b.state_dict()
+    assert set(sd_b) == {"state", "param_groups"} and len(sd_b["state"]) == len(list(b.parameters()))
+    assert sd_b["param_groups"][0]["params"] == list(range(len(list(b.parameters()))))
+    c = build(cfgd, b.state_dict()).train()
+    opt_c = torch.optim.Adam(c.parameters(), lr=1e-3)
+    opt_c.load_state_dict(sd_b)
+    assert opt_c.param_groups[0]["lr"] == 2e-3
+    steps(b, opt_b, 2, False)
+    steps(c, opt_c, 2, True)
+    for (k, p), (_, q) in zip(b.named_parameters(), c.named_parameters()):
+        assert rel_err(q.detach().cpu(), p.detach().cpu()) < 2e-3, k
+    # a fresh optimizer's state_dict is torch's empty one, and loading it resets the moments
+    fresh = FusedAdam(build(cfgd, sd).train(), lr=1e-3)
+    assert fresh.state_dict()["state"] == {}
+
+
+def test_graphed_step_warmup_leaves_no_trace_and_follows_lr_changes():
+    """GraphedTrainStep with its default warm-up: the first call must amount to ONE optimizer step (the warm-up steps
+    are undone), and halving the learning rate the way src/solver.py:169-176 does (optimizer.load_state_dict of an edited
+    state_dict) must take effect although lr is baked into the captured kernels (re-capture)."""
+    from conv_tasnet_b200 import cal_loss
+    from conv_tasnet_b200.graph import GraphedTrainStep
+    from conv_tasnet_b200.optim import FusedAdam
+    cfgd, sd, z = golden_model("gln")
+    mix, src = torch.from_numpy(z["mixture"]).cuda(), torch.from_numpy(z["source"]).cuda()
+    lens = torch.from_numpy(z["lengths"]).cuda()
+    lrs = [1e-3, 1e-3, 5e-4, 5e-4]
+
+    ref = build(cfgd, sd).train()
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    for lr in lrs:
+        opt_ref.param_groups[0]["lr"] = lr
+        est = ref(mix)
+        loss, *_ = cal_loss(src, est, lens)
+        opt_ref.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 5)
+        opt_ref.step()
+
+    model = build(cfgd, sd).train()
+    opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
+    step = GraphedTrainStep(model, opt)  # default warm-up (3 eager steps before the capture)
+    for i, lr in enumerate(lrs):
+        if lr != opt.lr:  # the solver's way of changing it
+            osd = opt.state_dict()
+            osd["param_groups"][0]["lr"] = lr
+            opt.load_state_dict(osd)
+        step(mix, src, lens)
+        assert step.captured
+        assert int(opt.step_count.item()) == i + 1
+    for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.detach().cpu(), q.detach().cpu()) < 2e-3, k
+
+
+def test_dispatcher_ops_match_the_module_and_pass_opcheck():
+    """torch.ops.ctn_b200.model_forward / pit_forward (conv_tasnet_b200.ops) against the nn.Module path: same outputs
+    bit for bit, same flat gradient, and torch.library.opcheck on schema / fake kernel / autograd registration."""
+    from conv_tasnet_b200 import cal_loss, ops
+    cfgd, sd, z = golden_model("gln")
+    model = build(cfgd, sd).train()
+    cfg = [cfgd[k] for k in ("N", "L", "B", "H", "P", "X", "R", "C")] + [0, 0, 0]
+    mix, src = torch.from_numpy(z["mixture"]).cuda(), torch.from_numpy(z["source"]).cuda()
+    lens = torch.from_numpy(z["lengths"]).cuda()
+    # module path
+    est_m = model(mix)
+    loss_m, snr_m, _, reorder_m = cal_loss(src, est_m, lens)
+    loss_m.backward()
+    g_m = model.flat_grads.clone()
+    # dispatcher path on the same flat parameters
+    fp = model.flat_params.detach().clone().requires_grad_(True)
+    est_o = ops.separate(fp, mix, cfg)
+    loss_o, snr_o, est_masked, reorder_o = ops.pit_loss(src, est_o, lens)
+    assert torch.equal(est_masked, est_m.detach()) and torch.equal(reorder_o, reorder_m) and torch.equal(snr_o, snr_m)
+    assert loss_o.item() == loss_m.item()
+    loss_o.backward()
+    assert rel_err(fp.grad.cpu(), g_m.cpu()) < 1e-6
+    with torch.no_grad():  # inference workspace
+        model.eval()
+        assert torch.equal(ops.separate(fp.detach(), mix, cfg), model(mix))
+    torch.library.opcheck(torch.ops.ctn_b200.model_forward.default, (fp.detach(), mix, cfg, False),
+                          test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(torch.ops.ctn_b200.model_forward.default, (fp.detach().requires_grad_(True), mix, cfg, True),
+                          test_utils=("test_schema", "test_autograd_registration", "test_faketensor"))
+    torch.library.opcheck(torch.ops.ctn_b200.pit_forward.default, (src, est_o.detach().clone(), lens),
+                          test_utils=("test_schema", "test_faketensor"))
