@@ -12,6 +12,9 @@ int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const fl
                    int, int, float*, double*, const float*, cudaStream_t);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
+int run_dwconv_bwd_gln_fused(const float*, const float*, const float*, NormStats, const float*, const double*, float*,
+                             const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int,
+                             int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
                         float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_apply(float*, const float*, const float*, NormStats, const float*, const double*, int, int, int,
@@ -183,6 +186,19 @@ int32_t ctn_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, c
                        float* dgamma1, float* dbeta1, double* red1, cudaStream_t stream) {
   return run_dwconv_bwd(dz2, z1, alpha1, make_stats(gln_acc1, rowstat1, K, H), gamma1, beta1, Wd, M, K, H, P, dilation,
                         causal, dn1, dWd, dgamma1, dbeta1, red1, nullptr, 0, stream);
+}
+
+int32_t ctn_dwconv_bwd_gln_fused(const float* dn2, const float* z2, const float* alpha2, const double* gln_acc2,
+                                 const float* gamma2, const double* red2, float* dalpha2, const float* z1,
+                                 const float* alpha1, const double* gln_acc1, const float* gamma1, const float* beta1,
+                                 const float* Wd, int32_t M, int32_t K, int32_t H, int32_t P, int32_t dilation,
+                                 int32_t causal, float* dn1, float* dWd, float* dgamma1, float* dbeta1, double* red1,
+                                 cudaStream_t stream) {
+  CTN_REQUIRE(dn2 && z2 && alpha2 && gln_acc2 && gamma2 && red2 && dalpha2 && z1 && alpha1 && gln_acc1 && gamma1 && beta1 &&
+              Wd && dn1 && dWd && dgamma1 && dbeta1, "dwconv_bwd_gln_fused: null pointer");
+  return run_dwconv_bwd_gln_fused(dn2, z2, alpha2, make_stats(gln_acc2, nullptr, K, H), gamma2, red2, dalpha2, z1, alpha1,
+                                  make_stats(gln_acc1, nullptr, K, H), gamma1, beta1, Wd, M, K, H, P, dilation, causal, dn1,
+                                  dWd, dgamma1, dbeta1, red1, nullptr, 0, stream);
 }
 
 int32_t ctn_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, const double* gln_acc,

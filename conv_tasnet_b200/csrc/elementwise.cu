@@ -336,6 +336,148 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
   }
 }
 
+// The same backward with the gLN backward of norm2 (+ the PReLU in front of it) applied ON LOAD: the kernel reads dn2 (the
+// gradient w.r.t. the normalised activation, as the pointwise-conv data gradient wrote it) and z2 and forms
+//   dz2 = r2 (dn2 gamma2 - m1 - yhat2 m2) prelu'(z2),   yhat2 = (prelu(z2) - mu2) r2,   (m1, m2) = red2 / (K H)
+// in registers as each frame enters the sliding window — the separate gln_bwd_apply pass over [F, H] (one read of dn2,
+// one of z2, one write of dz2, a launch) disappears; dalpha2 is summed over the frames a block owns as outputs.
+// Two channels per thread (8-byte accesses, 256 threads for H = 512: twice the warps of the 4-channel kernel and half
+// the registers per thread — the 4-channel version of this fusion spilled).  gLN only (per-sample scalars).
+template <int PT>
+__global__ void __launch_bounds__(256) dwconv_bwd_gln_fused_kernel(
+    const float* __restrict__ dn2, const float* __restrict__ z2, const float* __restrict__ alpha2, NormStats st2,
+    const float* __restrict__ gamma2, const double* __restrict__ red2, float* __restrict__ dalpha2,
+    const float* __restrict__ z1, const float* __restrict__ alpha1, NormStats st1, const float* __restrict__ gamma1,
+    const float* __restrict__ beta1, const float* __restrict__ Wd, int K, int H, int P, int dil, int cshift,
+    float* __restrict__ dn1, float* __restrict__ part, double* __restrict__ red1) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[3 * 32];
+  __shared__ float s_c[6];
+  const int m = blockIdx.y;
+  const int ncls = dw_classes(K, dil);
+  const int r = blockIdx.x % ncls, j0 = (blockIdx.x / ncls) * DW_TJ;
+  const int nclass = (K - r + dil - 1) / dil;
+  const int nj = max(0, min(DW_TJ, nclass - j0));
+  if (threadIdx.x == 0) {
+    float mu, rr;
+    load_stats(st1, m, 0, mu, rr);
+    s_c[0] = mu; s_c[1] = rr;
+    load_stats(st2, m, 0, mu, rr);
+    s_c[2] = mu; s_c[3] = rr;
+    const double cnt = (double)K * (double)H;
+    s_c[4] = (float)(red2[2 * m] / cnt);
+    s_c[5] = (float)(red2[2 * m + 1] / cnt);
+  }
+  __syncthreads();
+  const float mu1 = s_c[0], r1 = s_c[1], mu2 = s_c[2], r2 = s_c[3], m1 = s_c[4], m2 = s_c[5];
+  const float a1 = __ldg(alpha1), a2 = __ldg(alpha2);
+  const int64_t base = (int64_t)m * K;
+  constexpr int NP_ = PT ? PT : MAXP;
+  const int PP = PT ? PT : P;
+  float* prow = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)(PP + 2) * H;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
+    const float2 g = *reinterpret_cast<const float2*>(gamma1 + c), b = *reinterpret_cast<const float2*>(beta1 + c);
+    const float2 g2 = *reinterpret_cast<const float2*>(gamma2 + c);
+    float wd[2][NP_];
+    float2 dwd[NP_];
+#pragma unroll
+    for (int p = 0; p < NP_; ++p) {
+      wd[0][p] = p < PP ? Wd[c * PP + p] : 0.f;
+      wd[1][p] = p < PP ? Wd[(c + 1) * PP + p] : 0.f;
+      dwd[p] = make_float2(0.f, 0.f);
+    }
+    float sa = 0.f;  // dalpha2 partial
+    // dz2 of the sequence element idx from raw (dn2, z2); zero outside the sequence
+    auto dz_of = [&](int idx, const float2& d, const float2& zz) {
+      const int k = r + idx * dil;
+      if (!(idx >= 0 && k < K)) return make_float2(0.f, 0.f);
+      const float vx = prelu(zz.x, a2), vy = prelu(zz.y, a2);
+      float dax = r2 * (d.x * g2.x - m1 - (vx - mu2) * r2 * m2);
+      float day = r2 * (d.y * g2.y - m1 - (vy - mu2) * r2 * m2);
+      if (idx >= j0 && idx < j0 + nj)  // this block owns the frame as an output: count its PReLU-slope gradient once
+        sa += (zz.x > 0.f ? 0.f : dax * zz.x) + (zz.y > 0.f ? 0.f : day * zz.y);
+      return make_float2(dax * dprelu(zz.x, a2), day * dprelu(zz.y, a2));
+    };
+    auto ld2 = [&](const float* p, int idx) {
+      const int k = r + idx * dil;
+      return (idx >= 0 && k < K) ? *reinterpret_cast<const float2*>(p + (base + k) * H + c) : make_float2(0.f, 0.f);
+    };
+    // v[i] = dz2 at sequence index j + cshift - (PP-1) + i; tap p reads i = PP-1-p
+    float2 v[NP_];
+#pragma unroll
+    for (int i = 0; i < NP_; ++i) {
+      if (i < PP) {
+        const int idx = j0 + cshift - (PP - 1) + i;
+        v[i] = dz_of(idx, ld2(dn2, idx), ld2(z2, idx));
+      } else {
+        v[i] = make_float2(0.f, 0.f);
+      }
+    }
+    float2 dg = make_float2(0.f, 0.f), db = dg;
+    float s = 0.f, s2 = 0.f;
+    for (int jj = 0; jj < nj; jj += DW_U) {
+      float2 nd[DW_U], nz[DW_U], zc[DW_U];
+#pragma unroll
+      for (int u = 0; u < DW_U; ++u) {
+        const int idx = j0 + jj + u + cshift + 1;  // enters the window after output jj+u
+        nd[u] = ld2(dn2, idx);
+        nz[u] = ld2(z2, idx);
+        zc[u] = jj + u < nj ? ld2(z1, j0 + jj + u) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < DW_U; ++u) {
+        if (jj + u < nj) {
+          const float ax = prelu(zc[u].x, a1), ay = prelu(zc[u].y, a1);
+          const float2 yh = make_float2((ax - mu1) * r1, (ay - mu1) * r1);
+          const float2 n1 = make_float2(g.x * yh.x + b.x, g.y * yh.y + b.y);
+          float2 d = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int p = 0; p < NP_; ++p) {
+            if (p < PP) {
+              float2 t = v[0];
+#pragma unroll
+              for (int i = 1; i < NP_; ++i)
+                if (i == PP - 1 - p) t = v[i];
+              d.x = fmaf(wd[0][p], t.x, d.x); d.y = fmaf(wd[1][p], t.y, d.y);
+              dwd[p].x = fmaf(t.x, n1.x, dwd[p].x); dwd[p].y = fmaf(t.y, n1.y, dwd[p].y);
+            }
+          }
+          *reinterpret_cast<float2*>(dn1 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c) = d;
+          dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
+          db.x += d.x; db.y += d.y;
+          const float ghx = d.x * g.x, ghy = d.y * g.y;
+          s += ghx + ghy;
+          s2 += ghx * yh.x + ghy * yh.y;
+        }
+        const float2 nv = dz_of(j0 + jj + u + cshift + 1, nd[u], nz[u]);
+#pragma unroll
+        for (int i = 0; i + 1 < NP_; ++i) v[i] = v[i + 1];
+#pragma unroll
+        for (int i = 0; i < NP_; ++i)
+          if (i == PP - 1) v[i] = nv;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP_; ++p)
+      if (p < PP) *reinterpret_cast<float2*>(prow + (int64_t)p * H + c) = dwd[p];
+    *reinterpret_cast<float2*>(prow + (int64_t)PP * H + c) = dg;
+    *reinterpret_cast<float2*>(prow + (int64_t)(PP + 1) * H + c) = db;
+    acc[0] += (double)s;
+    acc[1] += (double)s2;
+    acc[2] += (double)sa;
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) {
+    if (red1 != nullptr) {
+      atomicAdd(red1 + 2 * m, acc[0]);
+      atomicAdd(red1 + 2 * m + 1, acc[1]);
+    }
+    atomicAdd(dalpha2, (float)acc[2]);
+  }
+}
+
 // fold `nb` partial rows of [Q][H] floats: q < P -> dW[c*P + q], q == P -> dgamma[c], q == P+1 -> dbeta[c]
 // grid (ceil(Q*H / 256), splits); each block sums a slice of the rows and adds it atomically (few atomics per output)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nb, int H, int P,
@@ -668,6 +810,33 @@ int run_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, NormS
     launch_kernel(dwconv_bwd_kernel<0>, grid, block_for_channels(H), 0, s, dz2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
   CTN_TRY(check_launch("dwconv_bwd_kernel"));
   if (defer_fold) return 0;  // the caller folds a whole stage's partial rows in one launch (run_fold_batch)
+  return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);
+}
+
+// dwconv backward with the gLN backward of norm2 fused on load (see dwconv_bwd_gln_fused_kernel); both norms gLN
+int run_dwconv_bwd_gln_fused(const float* dn2, const float* z2, const float* alpha2, NormStats st2, const float* gamma2,
+                             const double* red2, float* dalpha2, const float* z1, const float* alpha1, NormStats st1,
+                             const float* gamma1, const float* beta1, const float* Wd, int M, int K, int H, int P, int dil,
+                             int causal, float* dn1, float* dWd, float* dgamma1, float* dbeta1, double* red1, float* part,
+                             int defer_fold, cudaStream_t s) {
+  CTN_REQUIRE(H % 4 == 0 && P >= 1 && P <= MAXP, "dwconv_bwd: bad H/P (%d/%d)", H, P);
+  CTN_REQUIRE(st1.row == nullptr && st2.row == nullptr && st1.acc != nullptr && st2.acc != nullptr && red2 != nullptr,
+              "dwconv_bwd_gln_fused: both norms must be gLN (per-sample statistics)");
+  if (part == nullptr) {
+    void* scr = nullptr;
+    CTN_TRY(lib_scratch((size_t)dwconv_bwd_partial_floats(M, K, H, P, dil) * 4, &scr, 1));
+    part = reinterpret_cast<float*>(scr);
+  }
+  const int cshift = causal ? P - 1 : (P - 1) / 2;
+  const dim3 grid(dw_blocks(K, dil), M);
+  int threads = ((H / 2 + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (P == 3)
+    launch_kernel(dwconv_bwd_gln_fused_kernel<3>, grid, threads, 0, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
+  else
+    launch_kernel(dwconv_bwd_gln_fused_kernel<0>, grid, threads, 0, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
+  CTN_TRY(check_launch("dwconv_bwd_gln_fused_kernel"));
+  if (defer_fold) return 0;
   return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);
 }
 

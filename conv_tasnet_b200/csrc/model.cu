@@ -82,6 +82,9 @@ int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const fl
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
                         float*, double*, float*, int, cudaStream_t);
+int run_dwconv_bwd_gln_fused(const float*, const float*, const float*, NormStats, const float*, const double*, float*,
+                             const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int,
+                             int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int64_t dwconv_bwd_partial_floats(int M, int K, int H, int P, int dil);
 int64_t norm_bwd_partial_floats(int M, int K, int Ch);
 int dwconv_bwd_blocks(int M, int K, int dil);
@@ -139,7 +142,8 @@ static bool env_flag(const char* name) {
   return e != nullptr && e[0] == '1';
 }
 int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
-  // frame-major kernel (gemm_ts.cu): any O % 16 == 0; channel-major kernel (gemm_tc.cu, CTN_GEMM_SS=1): O % 128 == 0
+  // frame-major kernel (gemm_ts.cu): any O % 16 == 0; channel-major kernel (gemm_tc.cu): O % 128 == 0.
+  // CTN_GEMM_SS=1 (debug) never uses the frame-major kernel.
   static const bool use_ss = env_flag("CTN_GEMM_SS");
   const bool off_grid = use_ss ? (a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) : (a0.Kd % 64 != 0 || a0.O % 16 != 0);
   if (force_simt() || off_grid) return launch_gemm_simt(a0, s);
@@ -159,10 +163,21 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
       CTN_TRY(run_split_planes_tf32(a.W, (int64_t)a.O * a.Kd, 1, 0, const_cast<void*>(a.W_hi), const_cast<void*>(a.W_lo),
                                     0, s));
   }
-  // CTN_TS_MASK (debug): which flavours take the frame-major kernel: 1 = tf32 without fold, 2 = tf32 with fold, 4 = bf16
-  static const int ts_mask = getenv("CTN_TS_MASK") ? atoi(getenv("CTN_TS_MASK")) : 7;
+  // Which tcgen05 kernel: the frame-major one (gemm_ts.cu, activations in tensor memory) or the channel-major one
+  // (gemm_tc.cu).  Measured on B200 (profiles/r2_summary.md): for the bf16x3 flavours (data gradients, inference) the
+  // frame-major kernel is 1.3-1.5x faster once every SM has several frame tiles (F = 51k: 65 / 76 us against 99 / 101 us)
+  // and level at the headline's F = 9,597 (27 / 31 against 29.5 / 29.5 us: it wins the K = 256 "up" shape only); the TF32x3
+  // training forward needs two accumulators per output, cannot double-buffer them in 512 TMEM columns, and stays on
+  // the channel-major kernel.  Shapes off the 128-channel grid (O % 128 != 0) only exist in the frame-major kernel.
+  // CTN_TS_MASK (debug) overrides: 1 = tf32 without fold, 2 = tf32 with fold, 4 = bf16.
+  static const int ts_mask = getenv("CTN_TS_MASK") ? atoi(getenv("CTN_TS_MASK")) : -1;
   const int flavour = a.tf32 ? (a.c1 != nullptr ? 2 : 1) : 4;
-  if (!use_ss && (ts_mask & flavour) && ts_gemm_eligible(a)) {
+  bool want_ts;
+  if (use_ss) want_ts = false;
+  else if (ts_mask >= 0) want_ts = (ts_mask & flavour) != 0;
+  else want_ts = !a.tf32 && (a.F >= 16384 || a.O > a.Kd);
+  if (a.O % 128 != 0 || a.F < 16) want_ts = !use_ss;
+  if (want_ts && ts_gemm_eligible(a)) {
     const int rc = launch_gemm_ts(a, s);
     if (rc >= 0) return rc;
   }
@@ -615,11 +630,22 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       wa.alpha = X.blk(b, L.a2); wa.gamma = X.gam(b, 1); wa.beta = X.bet(b, 1); wa.st = st2;
       CTN_TRY(launch_wgrad(wa, s));
     }
-    CTN_TRY(norm_apply(b, 1, dn2, X.z2(b)));
-    CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K, c.H,
-                           c.P, dil, c.causal, dn1, gblk(b, L.Wd), bn ? X.bn_ab(b, 0, 1) : gblk(b, L.g1),
-                           bn ? X.bn_ab(b, 0, 0) : gblk(b, L.b1), gln ? X.red(b, 0) : nullptr,
-                           X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), bn ? 0 : 1, s));
+    // gLN: the backward of norm2 (+ PReLU) is elementwise given the per-sample sums, so the depthwise backward applies it
+    // as it loads dn2 / z2 (no gln_bwd_apply pass over [F, H]); cLN needs per-frame means, BatchNorm per-channel
+    // coefficients: they keep the separate apply pass.  CTN_NO_APPLY_FUSION=1 (debug) restores it for gLN too.
+    static const bool no_apply_fusion = env_flag("CTN_NO_APPLY_FUSION");
+    if (gln && !no_apply_fusion) {
+      CTN_TRY(run_dwconv_bwd_gln_fused(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), gblk(b, L.a2),
+                                       X.z1(b), X.blk(b, L.a1), st1, X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K, c.H,
+                                       c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1), X.red(b, 0),
+                                       X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), 1, s));
+    } else {
+      CTN_TRY(norm_apply(b, 1, dn2, X.z2(b)));
+      CTN_TRY(run_dwconv_bwd(dn2, X.z1(b), X.blk(b, L.a1), st1, X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K, c.H,
+                             c.P, dil, c.causal, dn1, gblk(b, L.Wd), bn ? X.bn_ab(b, 0, 1) : gblk(b, L.g1),
+                             bn ? X.bn_ab(b, 0, 0) : gblk(b, L.b1), gln ? X.red(b, 0) : nullptr,
+                             X.at<float>(p.part) + (int64_t)b * (p.part_dw + p.part_nr), bn ? 0 : 1, s));
+    }
     CTN_TRY(norm_apply(b, 0, dn1, X.z1(b)));
     {  // dW1 = dz1^T x
       WgradArgs wa = {};

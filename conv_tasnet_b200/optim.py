@@ -89,8 +89,10 @@ class FusedAdam:
         if int(self.step_count.item()) > 0:  # torch creates the per-parameter state lazily at the first step
             step = self.step_count.to(torch.float32).reshape(())
             for i, (p, o, n) in enumerate(zip(m._plist, offs, nums)):
-                state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[o:o + n].view(p.shape),
-                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape)}
+                # copies, not views: the flat moment buffers keep being updated in place, and torch's
+                # Optimizer.load_state_dict adopts the tensors it is given without copying them
+                state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         return {"state": state, "param_groups": [dict(self.param_groups[0])]}
 
     def load_state_dict(self, sd):

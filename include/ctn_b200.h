@@ -198,6 +198,16 @@ int32_t ctn_dwconv_bwd(const float* dz2, const float* z1, const float* alpha1, c
                        int32_t M, int32_t K, int32_t H, int32_t P, int32_t dilation, int32_t causal,
                        float* dn1, float* dWd, float* dgamma1, float* dbeta1, double* red1,
                        cudaStream_t stream);
+/* The same backward for gLN blocks with the backward of norm2 (+ its PReLU) applied on load (what ctn_norm_bwd_apply
+ * would do in a separate pass): takes dn2 (gradient w.r.t. the NORMALISED depthwise output), z2, the gLN statistics of
+ * prelu(z2), gamma2 and the per-sample sums red2 that ctn_norm_bwd_reduce left; dalpha2 [1] accumulates.
+ * (autograd of src/conv_tasnet.py:253-260,295,358-360 in one kernel.) */
+int32_t ctn_dwconv_bwd_gln_fused(const float* dn2, const float* z2, const float* alpha2, const double* gln_acc2,
+                                 const float* gamma2, const double* red2, float* dalpha2, const float* z1,
+                                 const float* alpha1, const double* gln_acc1, const float* gamma1,
+                                 const float* beta1, const float* Wd, int32_t M, int32_t K, int32_t H, int32_t P,
+                                 int32_t dilation, int32_t causal, float* dn1, float* dWd, float* dgamma1,
+                                 float* dbeta1, double* red1, cudaStream_t stream);
 /* norm backward, reduction pass: dgamma [Ch], dbeta [Ch], red [M,2] accumulate */
 int32_t ctn_norm_bwd_reduce(const float* dn, const float* z, const float* alpha, const double* gln_acc,
                             const float* rowstat, const float* gamma, int32_t M, int32_t K, int32_t Ch,

@@ -43,6 +43,39 @@ def _worker(rank, world, port, overlap):
     x = torch.arange(6).view(6, 1)
     (mine,) = shard_batch(rank, world, x)
     assert mine.flatten().tolist() == [3 * rank, 3 * rank + 1, 3 * rank + 2]
+    # uneven shards (the reference's batches vary in size, src/data.py:84-108): every rank's gradient is the mean over
+    # its own items; scaled by world * M_r / M_global and averaged, the result is the mean over the global batch
+    from conv_tasnet_b200.data_parallel import shard_sizes
+    assert shard_sizes(7, 2) == [4, 3] and shard_sizes(5, 3) == [2, 2, 1] and shard_sizes(6, 2) == [3, 3]
+    items = torch.arange(7, dtype=torch.float32)            # per-item "gradients" 0..6: global mean 3
+    (mine,) = shard_batch(rank, world, items)
+    assert mine.tolist() == ([0, 1, 2, 3] if rank == 0 else [4, 5, 6])
+    scale = dp.grad_scale_for(mine.numel(), torch.device("cpu"))
+    assert abs(scale.item() - world * mine.numel() / 7.0) < 1e-6
+    g.fill_(0)
+    g += mine.mean() * scale                                 # what the scaled backward leaves in the flat buffer
+    for stage in range(model.R + 2):
+        model._grad_sync(model, stage)
+    model._grad_sync(model, -1)
+    assert torch.allclose(g, torch.full_like(g, 3.0), rtol=1e-6), g[:4]
+    # a batch smaller than the world is refused on every rank alike (no rank may wait in a collective for another)
+    with pytest.raises(ValueError):
+        shard_batch(rank, world, torch.zeros(1, 3))
+    # the slow path (gradients computed aside): one synchronous whole-buffer reduce
+    aside = torch.full((5,), float(rank + 1))
+    model._grad_sync(model, -2, aside)
+    assert torch.allclose(aside, torch.full((5,), (1 + world) / 2.0)) and dp._pending == []
+    # utterance-sharded inference plans: disjoint, complete, balanced, identical on every rank
+    from conv_tasnet_b200.separate import batches_by_length, shard_utterances
+    lens = [480000, 31000, 64000, 479000, 8000, 250000, 250001, 12]
+    shards = [shard_utterances(lens, world, r) for r in range(world)]
+    assert sorted(sum(shards, [])) == list(range(len(lens)))
+    loads = [sum(lens[i] for i in sh) for sh in shards]
+    assert abs(loads[0] - loads[1]) <= max(lens)
+    assert all(lens[a] >= lens[b] for sh in shards for a, b in zip(sh, sh[1:]))  # longest first within a shard
+    for sh in shards:
+        for batch in batches_by_length(sh, lens, 3, 1000000):
+            assert len(batch) <= 3 and len(batch) * lens[batch[0]] <= 1000000 or len(batch) == 1
     # grad_views alias the flat buffer in parameters() order
     views = model.grad_views()
     assert sum(v.numel() for v in views) == sum(p.numel() for p in model.parameters())

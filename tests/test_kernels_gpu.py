@@ -384,3 +384,42 @@ def test_get_mask_matches_reference():
     assert got.shape == (4, 1, 37) and got.dtype == src.dtype
     assert torch.equal(got.cpu(), want)
     assert torch.equal(get_mask(src, lens.to(dev())).cpu(), want)  # lengths already on the device
+
+
+@pytest.mark.parametrize("causal,Pk,dil", [(False, 3, 1), (False, 3, 16), (True, 3, 4), (True, 2, 2), (False, 5, 2),
+                                           (False, 3, 128)])
+@pytest.mark.parametrize("M,K,H", [(2, 99, 16), (3, 400, 512), (1, 37, 8)])
+def test_dwconv_bwd_with_fused_gln_apply_equals_the_two_pass_schedule(causal, Pk, dil, M, K, H):
+    """ctn_dwconv_bwd_gln_fused (norm2 backward + PReLU' applied on load) against ctn_norm_bwd_apply followed by
+    ctn_dwconv_bwd — the schedule whose kernels are each checked against the oracle above — on the same inputs."""
+    z1, z2 = rnd(M, K, H, seed=31) + 0.1, rnd(M, K, H, seed=32) - 0.05
+    dn2 = rnd(M, K, H, seed=33)
+    g1, b1, g2, Wd = rnd(H, seed=34), rnd(H, seed=35), rnd(H, seed=36), rnd(H, Pk, seed=37)
+    a1, a2 = torch.tensor([0.25], device=dev()), torch.tensor([0.4], device=dev())
+    acc1 = gln_acc(FS.prelu(z1.cpu().double(), 0.25)).to(dev())
+    acc2 = gln_acc(FS.prelu(z2.cpu().double(), 0.4)).to(dev())
+    # the per-sample sums the reduce pass leaves for norm2
+    dg2, db2 = torch.zeros(H, device=dev()), torch.zeros(H, device=dev())
+    red2 = torch.zeros(M, 2, dtype=torch.float64, device=dev())
+    call("ctn_norm_bwd_reduce", P(dn2), P(z2), P(a2), P(acc2), None, P(g2), M, K, H, P(dg2), P(db2), P(red2))
+
+    def outputs():
+        return (torch.empty_like(z1), torch.zeros(H, Pk, device=dev()), torch.zeros(H, device=dev()),
+                torch.zeros(H, device=dev()), torch.zeros(M, 2, dtype=torch.float64, device=dev()),
+                torch.zeros(1, device=dev()))
+
+    # two passes
+    dn1_a, dWd_a, dg_a, db_a, red_a, dal_a = outputs()
+    dz2 = dn2.clone()
+    call("ctn_norm_bwd_apply", P(dz2), P(z2), P(a2), P(acc2), None, P(g2), P(red2), M, K, H, P(dal_a))
+    call("ctn_dwconv_bwd", P(dz2), P(z1), P(a1), P(acc1), None, P(g1), P(b1), P(Wd), M, K, H, Pk, dil, int(causal),
+         P(dn1_a), P(dWd_a), P(dg_a), P(db_a), P(red_a))
+    # fused
+    dn1_b, dWd_b, dg_b, db_b, red_b, dal_b = outputs()
+    call("ctn_dwconv_bwd_gln_fused", P(dn2), P(z2), P(a2), P(acc2), P(g2), P(red2), P(dal_b), P(z1), P(a1), P(acc1),
+         P(g1), P(b1), P(Wd), M, K, H, Pk, dil, int(causal), P(dn1_b), P(dWd_b), P(dg_b), P(db_b), P(red_b))
+    assert rel_err(dn1_b.cpu(), dn1_a.cpu()) < 1e-6
+    assert rel_err(dWd_b.cpu(), dWd_a.cpu()) < 1e-5
+    assert rel_err(dg_b.cpu(), dg_a.cpu()) < 1e-5 and rel_err(db_b.cpu(), db_a.cpu()) < 1e-5
+    assert rel_err(red_b.cpu(), red_a.cpu()) < 1e-6
+    assert abs(dal_b.item() - dal_a.item()) < 1e-4 * max(1.0, abs(dal_a.item()))
