@@ -336,13 +336,16 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
   }
 }
 
-// The same backward with the gLN backward of norm2 (+ the PReLU in front of it) applied ON LOAD: the kernel reads dn2 (the
+// The same backward with the gLN backward of norm2 (+ the PReLU in front of it) fused in: the kernel reads dn2 (the
 // gradient w.r.t. the normalised activation, as the pointwise-conv data gradient wrote it) and z2 and forms
 //   dz2 = r2 (dn2 gamma2 - m1 - yhat2 m2) prelu'(z2),   yhat2 = (prelu(z2) - mu2) r2,   (m1, m2) = red2 / (K H)
-// in registers as each frame enters the sliding window — the separate gln_bwd_apply pass over [F, H] (one read of dn2,
-// one of z2, one write of dz2, a launch) disappears; dalpha2 is summed over the frames a block owns as outputs.
-// Two channels per thread (8-byte accesses, 256 threads for H = 512: twice the warps of the 4-channel kernel and half
-// the registers per thread — the 4-channel version of this fusion spilled).  gLN only (per-sample scalars).
+// — the separate gln_bwd_apply pass over [F, H] (a read of dn2, a read of z2, a write of dz2, a launch) disappears.
+// Two phases per block.  Phase 1: the DW_TJ + P rows of the residue-class sequence the block's sliding window will
+// visit are converted by ALL threads as independent (row, 4-channel) items — many 16-byte loads in flight per thread —
+// into a shared-memory tile; dalpha2 is summed over the rows the block owns as outputs.  Phase 2: the sliding-window walk
+// of dwconv_bwd_kernel with the dz2 taps coming from that tile.  (Forming dz2 inside the register window instead —
+// tried in both rounds, 4 and 2 channels per thread — leaves too few loads in flight: 45 us against 21.6 + 12.7 us for
+// the two separate kernels.)  gLN only (per-sample scalars).
 template <int PT>
 __global__ void __launch_bounds__(256) dwconv_bwd_gln_fused_kernel(
     const float* __restrict__ dn2, const float* __restrict__ z2, const float* __restrict__ alpha2, NormStats st2,
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_gln_fused_kernel(
     float* __restrict__ dn1, float* __restrict__ part, double* __restrict__ red1) {
   pdl_launch_dependents();
   pdl_wait();
+  extern __shared__ __align__(16) float dz_s[];  // [DW_TJ + PP][H]: dz2 of sequence indices idx0 .. idx0 + DW_TJ + PP - 1
   __shared__ double red[3 * 32];
   __shared__ float s_c[6];
   const int m = blockIdx.y;
@@ -375,83 +379,106 @@ __global__ void __launch_bounds__(256) dwconv_bwd_gln_fused_kernel(
   const int64_t base = (int64_t)m * K;
   constexpr int NP_ = PT ? PT : MAXP;
   const int PP = PT ? PT : P;
-  float* prow = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)(PP + 2) * H;
+  const int idx0 = j0 + cshift - (PP - 1), nrows = DW_TJ + PP;
+  const int H4 = H >> 2;
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int c = threadIdx.x * 2; c < H; c += blockDim.x * 2) {
-    const float2 g = *reinterpret_cast<const float2*>(gamma1 + c), b = *reinterpret_cast<const float2*>(beta1 + c);
-    const float2 g2 = *reinterpret_cast<const float2*>(gamma2 + c);
-    float wd[2][NP_];
-    float2 dwd[NP_];
+  {  // ---- phase 1: dz2 tile ----
+    constexpr int U1 = 6;
+    float sa = 0.f;
+    const int items = nrows * H4;
+    for (int it0 = threadIdx.x; it0 < items; it0 += U1 * blockDim.x) {
+      float4 d[U1], zz[U1];
 #pragma unroll
-    for (int p = 0; p < NP_; ++p) {
-      wd[0][p] = p < PP ? Wd[c * PP + p] : 0.f;
-      wd[1][p] = p < PP ? Wd[(c + 1) * PP + p] : 0.f;
-      dwd[p] = make_float2(0.f, 0.f);
-    }
-    float sa = 0.f;  // dalpha2 partial
-    // dz2 of the sequence element idx from raw (dn2, z2); zero outside the sequence
-    auto dz_of = [&](int idx, const float2& d, const float2& zz) {
-      const int k = r + idx * dil;
-      if (!(idx >= 0 && k < K)) return make_float2(0.f, 0.f);
-      const float vx = prelu(zz.x, a2), vy = prelu(zz.y, a2);
-      float dax = r2 * (d.x * g2.x - m1 - (vx - mu2) * r2 * m2);
-      float day = r2 * (d.y * g2.y - m1 - (vy - mu2) * r2 * m2);
-      if (idx >= j0 && idx < j0 + nj)  // this block owns the frame as an output: count its PReLU-slope gradient once
-        sa += (zz.x > 0.f ? 0.f : dax * zz.x) + (zz.y > 0.f ? 0.f : day * zz.y);
-      return make_float2(dax * dprelu(zz.x, a2), day * dprelu(zz.y, a2));
-    };
-    auto ld2 = [&](const float* p, int idx) {
-      const int k = r + idx * dil;
-      return (idx >= 0 && k < K) ? *reinterpret_cast<const float2*>(p + (base + k) * H + c) : make_float2(0.f, 0.f);
-    };
-    // v[i] = dz2 at sequence index j + cshift - (PP-1) + i; tap p reads i = PP-1-p
-    float2 v[NP_];
+      for (int u = 0; u < U1; ++u) {
+        const int it = it0 + u * blockDim.x;
+        const int row = it / H4, c = (it - row * H4) << 2;
+        const int idx = idx0 + row, k = r + idx * dil;
+        const bool ok = it < items && idx >= 0 && k < K;
+        d[u] = ok ? ld4(dn2 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zz[u] = ok ? ld4(z2 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-    for (int i = 0; i < NP_; ++i) {
-      if (i < PP) {
-        const int idx = j0 + cshift - (PP - 1) + i;
-        v[i] = dz_of(idx, ld2(dn2, idx), ld2(z2, idx));
-      } else {
-        v[i] = make_float2(0.f, 0.f);
+      for (int u = 0; u < U1; ++u) {
+        const int it = it0 + u * blockDim.x;
+        if (it >= items) break;
+        const int row = it / H4, c = (it - row * H4) << 2;
+        const int idx = idx0 + row, k = r + idx * dil;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx >= 0 && k < K) {
+          const float4 g2 = ld4(gamma2 + c);
+          const float4 v = prelu4(zz[u], a2);
+          float4 da;
+          da.x = r2 * (d[u].x * g2.x - m1 - (v.x - mu2) * r2 * m2);
+          da.y = r2 * (d[u].y * g2.y - m1 - (v.y - mu2) * r2 * m2);
+          da.z = r2 * (d[u].z * g2.z - m1 - (v.z - mu2) * r2 * m2);
+          da.w = r2 * (d[u].w * g2.w - m1 - (v.w - mu2) * r2 * m2);
+          if (idx >= j0 && idx < j0 + nj)  // the block owns this frame as an output: count its PReLU-slope gradient once
+            sa += (zz[u].x > 0.f ? 0.f : da.x * zz[u].x) + (zz[u].y > 0.f ? 0.f : da.y * zz[u].y) +
+                  (zz[u].z > 0.f ? 0.f : da.z * zz[u].z) + (zz[u].w > 0.f ? 0.f : da.w * zz[u].w);
+          o = make_float4(da.x * dprelu(zz[u].x, a2), da.y * dprelu(zz[u].y, a2), da.z * dprelu(zz[u].z, a2),
+                          da.w * dprelu(zz[u].w, a2));
+        }
+        st4(dz_s + row * H + c, o);
       }
     }
-    float2 dg = make_float2(0.f, 0.f), db = dg;
+    acc[2] = (double)sa;
+  }
+  __syncthreads();
+  // ---- phase 2: the sliding-window walk, taps from the tile ----
+  float* prow = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)(PP + 2) * H;
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
+    float wd[4][NP_];
+    float4 dwd[NP_];
+#pragma unroll
+    for (int p = 0; p < NP_; ++p) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wd[j][p] = p < PP ? Wd[(c + j) * PP + p] : 0.f;
+      dwd[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // v[i] = dz2 at sequence index j + cshift - (PP-1) + i = tile row (j - j0) + i; tap p reads i = PP-1-p
+    float4 v[NP_];
+#pragma unroll
+    for (int i = 0; i < NP_; ++i) v[i] = i < PP ? ld4(dz_s + i * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s = 0.f, s2 = 0.f;
     for (int jj = 0; jj < nj; jj += DW_U) {
-      float2 nd[DW_U], nz[DW_U], zc[DW_U];
+      float4 zc[DW_U];
 #pragma unroll
       for (int u = 0; u < DW_U; ++u) {
-        const int idx = j0 + jj + u + cshift + 1;  // enters the window after output jj+u
-        nd[u] = ld2(dn2, idx);
-        nz[u] = ld2(z2, idx);
-        zc[u] = jj + u < nj ? ld2(z1, j0 + jj + u) : make_float2(0.f, 0.f);
+        const int k = r + (j0 + jj + u) * dil;
+        zc[u] = jj + u < nj ? ld4(z1 + (base + k) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < DW_U; ++u) {
         if (jj + u < nj) {
-          const float ax = prelu(zc[u].x, a1), ay = prelu(zc[u].y, a1);
-          const float2 yh = make_float2((ax - mu1) * r1, (ay - mu1) * r1);
-          const float2 n1 = make_float2(g.x * yh.x + b.x, g.y * yh.y + b.y);
-          float2 d = make_float2(0.f, 0.f);
+          const float4 a = prelu4(zc[u], a1);
+          const float4 yh = make_float4((a.x - mu1) * r1, (a.y - mu1) * r1, (a.z - mu1) * r1, (a.w - mu1) * r1);
+          const float4 n1 = make_float4(g.x * yh.x + b.x, g.y * yh.y + b.y, g.z * yh.z + b.z, g.w * yh.w + b.w);
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int p = 0; p < NP_; ++p) {
             if (p < PP) {
-              float2 t = v[0];
+              float4 t = v[0];
 #pragma unroll
               for (int i = 1; i < NP_; ++i)
                 if (i == PP - 1 - p) t = v[i];
               d.x = fmaf(wd[0][p], t.x, d.x); d.y = fmaf(wd[1][p], t.y, d.y);
+              d.z = fmaf(wd[2][p], t.z, d.z); d.w = fmaf(wd[3][p], t.w, d.w);
               dwd[p].x = fmaf(t.x, n1.x, dwd[p].x); dwd[p].y = fmaf(t.y, n1.y, dwd[p].y);
+              dwd[p].z = fmaf(t.z, n1.z, dwd[p].z); dwd[p].w = fmaf(t.w, n1.w, dwd[p].w);
             }
           }
-          *reinterpret_cast<float2*>(dn1 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c) = d;
+          st4(dn1 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c, d);
           dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y);
-          db.x += d.x; db.y += d.y;
-          const float ghx = d.x * g.x, ghy = d.y * g.y;
-          s += ghx + ghy;
-          s2 += ghx * yh.x + ghy * yh.y;
+          dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+          db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+          const float4 gh = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+          s += (gh.x + gh.y) + (gh.z + gh.w);
+          s2 += (gh.x * yh.x + gh.y * yh.y) + (gh.z * yh.z + gh.w * yh.w);
         }
-        const float2 nv = dz_of(j0 + jj + u + cshift + 1, nd[u], nz[u]);
+        // slide: the row that enters after output jj+u is tile row (jj + u) + PP (always inside the tile)
+        const float4 nv = ld4(dz_s + (jj + u + PP) * H + c);
 #pragma unroll
         for (int i = 0; i + 1 < NP_; ++i) v[i] = v[i + 1];
 #pragma unroll
@@ -461,12 +488,11 @@ __global__ void __launch_bounds__(256) dwconv_bwd_gln_fused_kernel(
     }
 #pragma unroll
     for (int p = 0; p < NP_; ++p)
-      if (p < PP) *reinterpret_cast<float2*>(prow + (int64_t)p * H + c) = dwd[p];
-    *reinterpret_cast<float2*>(prow + (int64_t)PP * H + c) = dg;
-    *reinterpret_cast<float2*>(prow + (int64_t)(PP + 1) * H + c) = db;
+      if (p < PP) st4(prow + (int64_t)p * H + c, dwd[p]);
+    st4(prow + (int64_t)PP * H + c, dg);
+    st4(prow + (int64_t)(PP + 1) * H + c, db);
     acc[0] += (double)s;
     acc[1] += (double)s2;
-    acc[2] += (double)sa;
   }
   block_sum<3>(acc, red);
   if (threadIdx.x == 0) {
@@ -829,12 +855,17 @@ int run_dwconv_bwd_gln_fused(const float* dn2, const float* z2, const float* alp
   }
   const int cshift = causal ? P - 1 : (P - 1) / 2;
   const dim3 grid(dw_blocks(K, dil), M);
-  int threads = ((H / 2 + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  if (P == 3)
-    launch_kernel(dwconv_bwd_gln_fused_kernel<3>, grid, threads, 0, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
-  else
-    launch_kernel(dwconv_bwd_gln_fused_kernel<0>, grid, threads, 0, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
+  const size_t smem = (size_t)(DW_TJ + P) * H * sizeof(float);
+  CTN_REQUIRE(smem <= 200 * 1024, "dwconv_bwd_gln_fused: H = %d needs %zu bytes of shared memory", H, smem);
+  if (P == 3) {
+    if (smem > 48 * 1024)
+      CTN_CUDA(cudaFuncSetAttribute(dwconv_bwd_gln_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(dwconv_bwd_gln_fused_kernel<3>, grid, block_for_channels(H), smem, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
+  } else {
+    if (smem > 48 * 1024)
+      CTN_CUDA(cudaFuncSetAttribute(dwconv_bwd_gln_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(dwconv_bwd_gln_fused_kernel<0>, grid, block_for_channels(H), smem, s, dn2, z2, alpha2, st2, gamma2, red2, dalpha2, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, dn1, part, red1);
+  }
   CTN_TRY(check_launch("dwconv_bwd_gln_fused_kernel"));
   if (defer_fold) return 0;
   return fold_partials(part, grid.x * grid.y, H, P, dWd, dgamma1, dbeta1, s);

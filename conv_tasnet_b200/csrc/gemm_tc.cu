@@ -507,7 +507,7 @@ constexpr int WGT = CTN_WGT;               // threads of one converter group
 constexpr int WNG = CTN_WNG;               // converter groups, taking k-blocks round robin
 constexpr int W_THREADS = 128 + WNG * WGT; // 4 control warps + the converter / epilogue warps
 template <int NI>
-__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
+__global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dw, TcWgradArgs a) {
   pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -666,16 +666,44 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
         fence_proxy_async();
         mbar_arrive(full + s);
       }
-      // ---- epilogue: atomically add the partial tile ----
+      // ---- epilogue: add the partial tile to dW with TMA reductions ----
       mbar_wait(tmem_full, 0);
       tc_fence_after();
-      // TMEM gives lane = output row o, registers = columns i: adding from there would scatter every warp instruction
-      // over 32 rows.  Each warp therefore stages its [32 rows x NI/2 columns] quadrant in shared memory (the operand
-      // stages are free: every MMA has completed) and adds it row-wise, 512 contiguous bytes per warp instruction.
+      // TMEM gives lane = output row o, registers = columns i.  The tile is staged in shared memory (the operand stages
+      // are free: every MMA has completed) as NI/32 boxes of [128 rows x 128 bytes] in the 128-byte-swizzle layout
+      // (conflict-free 16-byte stores down a column), and one thread hands each box to the TMA engine as a bulk
+      // reduce-add into dW (cp.reduce.async.bulk.tensor): the L2 does the additions at line granularity while the CTA
+      // retires, instead of 32k red.global.add.v4 issued and waited for by the warps (measured: the split-K atomics were
+      // ~10k of the kernel's ~37k cycles).  CTN_WGRAD_RED=1 (compile time) keeps the red.v4 path for A/B.
       constexpr int EW = (WNG * WGT / 32) >= 16 ? 16 : 8;  // epilogue warps (the first EW converter warps)
       constexpr int CSPLIT = EW / 4;  // warps sharing a TMEM lane quarter: each takes NI / CSPLIT columns
       constexpr int QC = NI / CSPLIT;
       const int q = warp & 3, part = (warp - 4) >> 2;
+#ifndef CTN_WGRAD_RED
+      if (warp - 4 < EW) {
+        const int jb = part * QC, je = jb + QC;
+        const int row = q * 32 + lane;
+        for (int j = jb; j < je; j += 8) {
+          float acc[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j, acc);
+          const uint32_t box = smem_base + (uint32_t)((j >> 5) * (BM * 128) + row * 128);
+          const int c = (j & 31) >> 2;  // 16-byte chunk inside the 128-byte box row
+          sts128(box + (uint32_t)(((c ^ (row & 7)) << 4)), make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]),
+                                                                       __float_as_uint(acc[2]), __float_as_uint(acc[3])));
+          sts128(box + (uint32_t)((((c + 1) ^ (row & 7)) << 4)), make_uint4(__float_as_uint(acc[4]), __float_as_uint(acc[5]),
+                                                                             __float_as_uint(acc[6]), __float_as_uint(acc[7])));
+        }
+        fence_proxy_async();  // the generic-proxy stores above must be visible to the TMA engine (async proxy)
+        asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
+        if (warp == 4 && lane == 0) {
+#pragma unroll 1
+          for (int b = 0; b < NI / 32; ++b)
+            tma_reduce_add_2d(&map_dw, smem + b * (BM * 128), i0 + 32 * b, o0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go once the engine has read it
+        }
+      }
+#else
       if (warp - 4 < EW) {
       const int jb = part * QC, je = jb + QC;
       constexpr int PITCH = NI + 4;  // floats; 16-byte row alignment, conflict-free 16-byte stores down a column
@@ -699,6 +727,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(TcWgradArgs a) {
         red_add_v4(a.dW + (int64_t)(o0 + row) * a.I + i0 + col, v.x, v.y, v.z, v.w);
       }
       }
+#endif
     }
   }
   tc_fence_before();
@@ -934,12 +963,24 @@ int launch_wgrad_tc(const WgradArgs& w, cudaStream_t s) {
     CTN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_mask |= 1ull << (dev & 63);
   }
+  CUtensorMap md;  // dW [O, I] fp32, boxes of [128 rows x 32 floats], 128-byte swizzle: the target of the TMA reduce-adds
+  {
+    EncodeTiledFn enc = get_encode();
+    CTN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)w.I, (cuuint64_t)w.O};
+    const cuuint64_t strides[1] = {(cuuint64_t)w.I * 4};
+    const cuuint32_t box[2] = {32, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&md, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CTN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (dW) failed with code %d", (int)r);
+  }
   if (ni == 256) {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 256 * 2) + 128 + 8 * WG_STAT_CACHE;
-    launch_kernel(tc_wgrad_kernel<256>, grid, W_THREADS, smem, s, a);
+    launch_kernel(tc_wgrad_kernel<256>, grid, W_THREADS, smem, s, md, a);
   } else {
     const size_t smem = (size_t)WSTAGES * (2 * WK * BM * 2 + 2 * WK * 128 * 2) + 128 + 8 * WG_STAT_CACHE;
-    launch_kernel(tc_wgrad_kernel<128>, grid, W_THREADS, smem, s, a);
+    launch_kernel(tc_wgrad_kernel<128>, grid, W_THREADS, smem, s, md, a);
   }
   return check_launch(w.gamma != nullptr ? "tc_wgrad_kernel (norm prologue)" : "tc_wgrad_kernel (plain)");
 }

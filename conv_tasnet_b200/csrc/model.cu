@@ -3,6 +3,8 @@
 // of kernel launches on one stream (graph-capturable: no allocation, no host sync, no host-side
 // data-dependent control flow).
 #include <stdarg.h>
+
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -122,18 +124,30 @@ static bool force_simt() {
   return v == 1;
 }
 
+// Library-owned device scratch of the STAND-ALONE single-kernel entry points (weight planes, partial rows); the
+// whole-model path never comes here (it works in the caller's workspace).  One buffer per (device, slot, calling
+// thread) — two host threads driving one device never share a buffer — grown under a mutex; growing synchronises the
+// device first (cudaFree of the old buffer would do so anyway: an earlier launch of this thread may still read it).
 int lib_scratch(size_t bytes, void** out, int slot) {
-  static void* buf[16][2] = {{nullptr}};
-  static size_t cap[16][2] = {{0}};
+  struct Slot { void* buf; size_t cap; };
+  static thread_local Slot slots[16][2] = {};
+  static std::mutex mu;
   int dev = 0;
   CTN_CUDA(cudaGetDevice(&dev));
   CTN_REQUIRE(dev < 16 && slot >= 0 && slot < 2, "lib_scratch: bad device/slot");
-  if (cap[dev][slot] < bytes) {
-    if (buf[dev][slot]) CTN_CUDA(cudaFree(buf[dev][slot]));
-    CTN_CUDA(cudaMalloc(&buf[dev][slot], bytes));
-    cap[dev][slot] = bytes;
+  Slot& sl = slots[dev][slot];
+  if (sl.cap < bytes) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (sl.buf) {
+      CTN_CUDA(cudaDeviceSynchronize());
+      CTN_CUDA(cudaFree(sl.buf));
+      sl.buf = nullptr;
+      sl.cap = 0;
+    }
+    CTN_CUDA(cudaMalloc(&sl.buf, bytes));
+    sl.cap = bytes;
   }
-  *out = buf[dev][slot];
+  *out = sl.buf;
   return 0;
 }
 
@@ -630,11 +644,12 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       wa.alpha = X.blk(b, L.a2); wa.gamma = X.gam(b, 1); wa.beta = X.bet(b, 1); wa.st = st2;
       CTN_TRY(launch_wgrad(wa, s));
     }
-    // gLN: the backward of norm2 (+ PReLU) is elementwise given the per-sample sums, so the depthwise backward applies it
-    // as it loads dn2 / z2 (no gln_bwd_apply pass over [F, H]); cLN needs per-frame means, BatchNorm per-channel
-    // coefficients: they keep the separate apply pass.  CTN_NO_APPLY_FUSION=1 (debug) restores it for gLN too.
-    static const bool no_apply_fusion = env_flag("CTN_NO_APPLY_FUSION");
-    if (gln && !no_apply_fusion) {
+    // gLN: the backward of norm2 (+ PReLU) is elementwise given the per-sample sums, so the depthwise backward can apply
+    // it while it loads dn2 / z2 (no gln_bwd_apply pass over [F, H]).  Built, parity-tested and measured: the fused kernel
+    // saves a launch and 2 H elements per frame of traffic but lowers the step from 5.95 to 6.08 ms (elementwise.cu), so it
+    // is opt-in (CTN_APPLY_FUSION=1).  cLN needs per-frame means and BatchNorm per-channel coefficients: separate pass.
+    static const bool apply_fusion = env_flag("CTN_APPLY_FUSION");
+    if (gln && apply_fusion) {
       CTN_TRY(run_dwconv_bwd_gln_fused(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), gblk(b, L.a2),
                                        X.z1(b), X.blk(b, L.a1), st1, X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K, c.H,
                                        c.P, dil, c.causal, dn1, gblk(b, L.Wd), gblk(b, L.g1), gblk(b, L.b1), X.red(b, 0),
