@@ -46,9 +46,10 @@ CONFIGS = {
             workload=f"configs[0]: paper config {PAPER_STR} C=2 gLN non-causal, one 4 s @ 8 kHz mixture, fp32 forward + cal_loss"),
     1: dict(model={}, M=3, seconds=4, mode="train",
             workload=f"configs[1]: paper config {PAPER_STR} C=2 gLN non-causal, batch 3 per GPU x 4 s @ 8 kHz, {TRAIN_STR}"),
-    2: dict(model=dict(norm_type="cLN", causal=True), M=32, seconds=4, mode="fwd",
+    2: dict(model=dict(norm_type="cLN", causal=True), M=32, seconds=4, mode="fwd", dtype="bf16",
             workload=f"configs[2]: causal cLN variant (causal=1, norm_type=cLN, Chomp1d) of the paper config {PAPER_STR} C=2, "
-                     "batch 32 per GPU x 4 s @ 8 kHz, forward"),
+                     "batch 32 per GPU x 4 s @ 8 kHz, bf16 forward (H-wide activations stored as bf16, single-bf16 MMAs, "
+                     "fp32 accumulation / residual stream / statistics / I-O)"),
     3: dict(model=dict(C=3), M=16, seconds=4, mode="train",
             workload=f"configs[3]: 3-speaker (C=3, 6-permutation PIT) paper config {PAPER_STR} gLN non-causal, batch 16 per GPU x 4 s "
                      f"@ 8 kHz, {TRAIN_STR}"),
@@ -254,6 +255,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
     ap.add_argument("--mode", default=None, choices=["train", "fwd", "fwd_loss"])
+    ap.add_argument("--dtype", default=None, choices=["f32", "bf16"], help="forward modes only: bf16 = the reduced-precision "
+                    "inference path (default: the config's own, bf16 for --config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run only warm-up + K device-resident steps (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
@@ -261,7 +264,13 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     mode = args.mode or CONFIGS[args.config]["mode"]
+    dtype = args.dtype or CONFIGS[args.config].get("dtype", "f32")
+    if mode == "train":
+        dtype = "f32"  # the reference trains in fp32 and so does this path
 
+    if os.environ.get("BENCH_WATCHDOG"):  # debug: dump every thread's Python stack if the run is still going after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=False)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -291,6 +300,8 @@ def main():
     torch.manual_seed(0)
     model = ConvTasNet(**kw).cuda()
     model.train() if train else model.eval()
+    if dtype == "bf16":
+        model.half_inference(True)
     # data parallel training shards the batch and all-reduces gradients; inference shards by utterance with no collective
     dp = ShardedDataParallel(model) if (world > 1 and train) else model
     opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0) if train else None
@@ -456,6 +467,7 @@ def main():
         def kern():
             _lib.check(L.ctn_conv1x1_planes(Am.data_ptr(), hi.data_ptr(), lo.data_ptr(), 0, Dm.data_ptr(), F, Hc, Bc, K,
                                             st))
+        # (timed in the bf16x3 flavour for every forward config: the bf16 path's single-plane conv is its cheaper sibling)
         kname, ksub = ("1x1-conv GEMM z1[F,512] = x[F,256] W1^T (tcgen05, bf16x3 split of the inference forward, "
                        "pre-split weight planes)"), "gemm_kernel"
         n_launch = 2 * kw["R"] * kw["X"] + 2
@@ -499,7 +511,7 @@ def main():
 
     line = {"metric": METRIC[mode], "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config_dict(args.config, mode, world),
             "e2e": {"value": audio / secs_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": secs_e2e / args.steps * 1e3, "last_result": last},

@@ -147,6 +147,9 @@ class ConvTasNet(nn.Module):
         self._layout = None
         self._ws_cache = {}       # training flag -> (grow-only workspace, weakref of the autograd token using it)
         self._ws_override = None  # set by graph.GraphedTrainStep / GraphedInference: the graph owns its workspace
+        # torch.bfloat16: no_grad forwards store the H-wide activations as bf16 and use single-bf16 MMAs ("bf16 forward",
+        # BASELINE configs[2]; opt-in — the reference has no reduced-precision path, outputs stay within 2e-2 of fp32)
+        self.inference_dtype = torch.float32
         self._grad_sync = None  # set by data_parallel.ShardedDataParallel
         self._grad_scale = None  # set per forward by ShardedDataParallel (uneven shards), consumed by the backward
         self._overwrite_next = False  # set by optim.FusedAdam: the next backward overwrites the flat gradients
@@ -297,9 +300,9 @@ class ConvTasNet(nn.Module):
                 if self.training:
                     self._bn_count += 1
             else:
+                mode = 1 if training else (2 if self.inference_dtype == torch.bfloat16 else 0)
                 _lib.check(_lib.lib().ctn_model_forward(ctypes.byref(self._cfg), _lib.ptr(flat), _lib.ptr(mixture), M,
-                                                        T, _lib.ptr(est), _lib.ptr(ws), ws.numel(),
-                                                        1 if training else 0, _lib.stream()))
+                                                        T, _lib.ptr(est), _lib.ptr(ws), ws.numel(), mode, _lib.stream()))
         token = None
         if training:
             token = _Token()
@@ -360,6 +363,15 @@ class ConvTasNet(nn.Module):
             _lib.check(_lib.lib().ctn_model_backward_stage(
                 ctypes.byref(self._cfg), _lib.ptr(self._flat), _lib.ptr(mixture), M, T, _lib.ptr(d_est),
                 _lib.ptr(grads), _lib.ptr(ws), ws.numel(), 0, stage, _lib.stream()))
+
+    def half_inference(self, enabled=True):
+        """Opt into the reduced-precision inference path: no_grad forwards keep the H-wide activations in bf16 and feed
+        the tensor cores single bf16 operands (fp32 accumulation, fp32 residual stream / statistics / I/O).  Training
+        and forwards under autograd are unaffected.  Returns self."""
+        if enabled and (self._bns or self.N % 64 or self.B % 64 or self.H % 64):
+            raise ValueError("half_inference needs gLN / cLN and N, B, H multiples of 64")
+        self.inference_dtype = torch.bfloat16 if enabled else torch.float32
+        return self
 
     def grad_bucket(self, stage):
         off, cnt = ctypes.c_int64(), ctypes.c_int64()

@@ -5,11 +5,11 @@
 namespace ctn {
 int run_encoder_fwd(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int run_encoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
-int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t);
+int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t, int bf16 = 0);
 int run_prep_normfold(const float*, const float*, const float*, int, int, int, int64_t, float*, float*, float*, int64_t,
                       int64_t, cudaStream_t);
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
-                   int, int, float*, double*, const float*, cudaStream_t);
+                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_dwconv_bwd_gln_fused(const float*, const float*, const float*, NormStats, const float*, const double*, float*,
@@ -146,13 +146,16 @@ int32_t ctn_conv1x1(const float* A, const float* W, int32_t w_is_kn, float* D, i
   return launch_gemm(a, stream);
 }
 
-int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t tf32, float* D, int64_t F, int32_t O,
+int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t mode, float* D, int64_t F, int32_t O,
                            int32_t Kd, int32_t K, cudaStream_t stream) {
-  CTN_REQUIRE(A && W_hi && W_lo && D, "conv1x1_planes: null pointer");
+  CTN_REQUIRE(A && W_hi && D && (W_lo || mode >= 2), "conv1x1_planes: null pointer");
+  CTN_REQUIRE(mode >= 0 && mode <= 4, "conv1x1_planes: mode must be 0..4 (got %d)", mode);
   CTN_REQUIRE(Kd % 64 == 0 && O % 16 == 0, "conv1x1_planes: needs Kd %% 64 == 0 and O %% 16 == 0 (got Kd=%d O=%d)", Kd, O);
   GemmArgs a = {};
   a.A = A; a.D = D; a.F = F; a.O = O; a.Kd = Kd; a.K = K;
-  a.W_hi = W_hi; a.W_lo = W_lo; a.tf32 = tf32 ? 1 : 0;
+  a.W_hi = W_hi; a.W_lo = W_lo; a.tf32 = mode == 1 ? 1 : 0;
+  a.half = mode >= 2 ? (mode == 4 ? 2 : 1) : 0;
+  a.d_bf16 = mode == 3 ? 1 : 0;
   return launch_gemm(a, stream);
 }
 

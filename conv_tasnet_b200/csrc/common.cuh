@@ -171,6 +171,11 @@ struct GemmArgs {
   const void* W_hi;
   const void* W_lo;
   int tf32;  // 1: planes are fp32 (tf32 hi + exact remainder), forward precision; 0: bf16 hi/lo planes
+  // reduced-precision inference (frame-major kernel only; BASELINE configs[2] "bf16 forward"): one bf16 plane per operand.
+  // half = 1: A is fp32 in memory, rounded to bf16 on the way in; half = 2: A is STORED as bf16 ([F, Kd] bf16, the pointer
+  // travels in `A`); d_bf16 = 1: D is stored as bf16 ([F, O] bf16 behind the `D` pointer).  W_lo is not read.
+  int half;
+  int d_bf16;
   // optional fused norm-backward reduction on the OUTPUT (D = dn, the gradient w.r.t. a normalised activation):
   // with yhat = (prelu(nred_z, nred_alpha) - mu) * r (stats in `st`):  dgamma[o] += sum_f D*yhat, dbeta[o] += sum_f D,
   // red[m] += (sum D*gamma, sum D*gamma*yhat).  nred_part: scratch for the un-fused fallback.

@@ -2,6 +2,8 @@
 // statistics, norm + dilated depthwise conv (+Chomp1d) forward/backward, gLN/cLN (+PReLU) backward,
 // mask nonlinearity + decoder basis + overlap-add forward/backward, norm-fold weight prep.
 // All activations are channels-last [M, K, Ch]; every global access is a 16-byte vector along channels.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ctn {
@@ -9,6 +11,19 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// the same 4-channel accesses on a bf16 tensor (reduced-precision inference stores the H-wide activations as bf16)
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                     __uint_as_float(w.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 w;
+  w.x = *reinterpret_cast<const uint32_t*>(&a);
+  w.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = w;
+}
 __device__ __forceinline__ float4 prelu4(float4 v, float a) {
   return make_float4(prelu(v.x, a), prelu(v.y, a), prelu(v.z, a), prelu(v.w, a));
 }
@@ -17,7 +32,8 @@ __device__ __forceinline__ float dprelu(float z, float a) { return z > 0.f ? 1.f
 // ---------------------------------------------------------------------------------------
 // cLN statistics: one warp per frame, two-pass like torch.var (src/conv_tasnet.py:332-333)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+template <typename T>
+__global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha,
                                                         int64_t F, int Ch, float* __restrict__ rowstat) {
   pdl_launch_dependents();
   pdl_wait();
@@ -26,7 +42,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
   if (f >= F) return;
   const bool hasp = alpha != nullptr;
   const float a = hasp ? __ldg(alpha) : 1.f;
-  const float* row = x + f * Ch;
+  const T* row = x + f * Ch;
   float s = 0.f;
   for (int c = lane * 4; c < Ch; c += 128) {
     float4 v = ld4(row + c);
@@ -117,12 +133,12 @@ __host__ __device__ inline int dw_blocks(int K, int dil, int tj = DW_TJ) {
   return ncls * ((per_class + tj - 1) / tj);
 }
 
-template <int PT>
-__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ alpha1,
+template <int PT, typename T = float>
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ z1, const float* __restrict__ alpha1,
                                                          NormStats st1, const float* __restrict__ gamma1,
                                                          const float* __restrict__ beta1, const float* __restrict__ Wd,
                                                          int K, int H, int P, int dil, int cshift,
-                                                         float* __restrict__ z2, double* __restrict__ stat_out,
+                                                         T* __restrict__ z2, double* __restrict__ stat_out,
                                                          const float* __restrict__ alpha2) {
   pdl_launch_dependents();
   pdl_wait();
@@ -189,6 +205,10 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
           for (int p = 0; p < NP_; ++p) {
             o.x = fmaf(wd[0][p], w[p].x, o.x); o.y = fmaf(wd[1][p], w[p].y, o.y);
             o.z = fmaf(wd[2][p], w[p].z, o.z); o.w = fmaf(wd[3][p], w[p].w, o.w);
+          }
+          if (sizeof(T) == 2) {  // bf16 storage: the statistics describe the values the consumers will read
+            o.x = __bfloat162float(__float2bfloat16_rn(o.x)); o.y = __bfloat162float(__float2bfloat16_rn(o.y));
+            o.z = __bfloat162float(__float2bfloat16_rn(o.z)); o.w = __bfloat162float(__float2bfloat16_rn(o.w));
           }
           st4(z2 + (base + r + (int64_t)(j0 + jj + u) * dil) * H + c, o);
           if (do_stats) {
@@ -752,9 +772,12 @@ static int block_for_channels(int Ch) {
 // ---------------------------------------------------------------------------------------
 // host launchers (C linkage wrappers live in c_api.cu)
 // ---------------------------------------------------------------------------------------
-int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s) {
+int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s, int bf16) {
   CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
-  launch_kernel(row_stats_kernel, cdiv(F, 8), 256, 0, s, x, alpha, F, Ch, rowstat);
+  if (bf16)
+    launch_kernel(row_stats_kernel<__nv_bfloat16>, cdiv(F, 8), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), alpha, F, Ch, rowstat);
+  else
+    launch_kernel(row_stats_kernel<float>, cdiv(F, 8), 256, 0, s, x, alpha, F, Ch, rowstat);
   return check_launch("row_stats_kernel");
 }
 
@@ -766,12 +789,21 @@ int run_prep_normfold(const float* W, const float* gamma, const float* beta, int
 
 int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const float* gamma1, const float* beta1,
                    const float* Wd, int M, int K, int H, int P, int dil, int causal, float* z2, double* stat_out,
-                   const float* alpha2, cudaStream_t s) {
+                   const float* alpha2, cudaStream_t s, int bf16) {
   CTN_REQUIRE(H % 4 == 0, "dwconv: H must be a multiple of 4 (got %d)", H);
   CTN_REQUIRE(P >= 1 && P <= MAXP, "dwconv: kernel size P must be in [1,%d] (got %d)", MAXP, P);
   CTN_REQUIRE(causal || (P % 2 == 1), "dwconv: non-causal needs odd P (reference output length changes otherwise)");
   const int cshift = causal ? P - 1 : (P - 1) / 2;
   const dim3 grid(dw_blocks(K, dil, DWF_TJ), M);
+  if (bf16) {  // reduced-precision inference: z1 and z2 are stored as bf16 (the pointers are reinterpreted)
+    const __nv_bfloat16* zi = reinterpret_cast<const __nv_bfloat16*>(z1);
+    __nv_bfloat16* zo = reinterpret_cast<__nv_bfloat16*>(z2);
+    if (P == 3)
+      launch_kernel(dwconv_fwd_kernel<3, __nv_bfloat16>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
+    else
+      launch_kernel(dwconv_fwd_kernel<0, __nv_bfloat16>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
+    return check_launch("dwconv_fwd_kernel<bf16>");
+  }
   if (P == 3)
     launch_kernel(dwconv_fwd_kernel<3>, grid, block_for_channels(H), 0, s, z1, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, z2, stat_out, alpha2);
   else

@@ -24,7 +24,11 @@
 // is transposed through a swizzled shared-memory buffer so that global stores (and the residual loads) are whole
 // 128-byte rows.
 //
-// Precision: as gemm_tc.cu — TF32x3 for the training forward (the correction products lo*hi + hi*lo in their own
+// Reduced-precision inference (HALF > 0, the "bf16 forward" of BASELINE configs[2]; no reference path, 2e-2 budget):
+// ONE bf16 plane per operand and one MMA per k-step; the activations are either fp32 in memory and rounded by the
+// converters (HALF = 1) or STORED as bf16 (HALF = 2: half the bytes, the converter only applies the PReLU), and the output
+// can be stored as bf16 (DBF) — the two H-wide tensors of a block (z1, z2) then cost 2 bytes per element end to end.
+// Precision otherwise: as gemm_tc.cu — TF32x3 for the training forward (the correction products lo*hi + hi*lo in their own
 // accumulator), bf16x3 for data gradients and inference.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -97,16 +101,19 @@ struct SegIter {
   }
 };
 
-template <bool TF32, bool FOLD, bool RES, bool STATS>
+template <bool TF32, bool FOLD, bool RES, bool STATS, int HALF = 0, bool DBF = false>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_a, TsGemmArgs a) {
+  static_assert(!(TF32 && HALF), "the single-plane mode is a bf16 flavour");
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int KB = TF32 ? 32 : 64;                        // K elements per k-block (128 bytes of a weight row)
-  constexpr int RAW_STAGE = TF32 ? TS_RAW_BOX : 2 * TS_RAW_BOX;
+  // raw activation stage: 32 fp32 per row (TF32), 64 fp32 = two boxes (bf16 from fp32), or 64 bf16 = one box (HALF = 2)
+  constexpr int RAW_STAGE = (TF32 || HALF == 2) ? TS_RAW_BOX : 2 * TS_RAW_BOX;
   constexpr int NACC = TF32 ? 2 : 1;                        // accumulators per output (main, correction)
+  constexpr int NPL = HALF ? 1 : 2;                         // operand planes (hi, lo)
   const int WST = a.w_stages, RST = a.raw_stages, AST = a.a_stages, ND = a.nd;
-  const int w_plane = a.nmax * 128, w_stage = 2 * w_plane;
+  const int w_plane = a.nmax * 128, w_stage = NPL * w_plane;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t raw_base = smem_base + WST * w_stage;
   const uint32_t epi_base = raw_base + RST * RAW_STAGE;
@@ -183,10 +190,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           mbar_expect_tx(w_full + ws, w_stage);  // all the slices land here
           if (CL > 1) {
             tma_load_2d_mc(st, &map_hi, w_full + ws, kb * KB, s.c0 + rank * slice, cmask);
-            tma_load_2d_mc(st + w_plane, &map_lo, w_full + ws, kb * KB, s.c0 + rank * slice, cmask);
+            if (NPL == 2) tma_load_2d_mc(st + w_plane, &map_lo, w_full + ws, kb * KB, s.c0 + rank * slice, cmask);
           } else {
             tma_load_2d(st, &map_hi, w_full + ws, kb * KB, s.c0);
-            tma_load_2d(st + w_plane, &map_lo, w_full + ws, kb * KB, s.c0);
+            if (NPL == 2) tma_load_2d(st + w_plane, &map_lo, w_full + ws, kb * KB, s.c0);
           }
         }
       }
@@ -204,7 +211,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           uint8_t* dst = smem + WST * w_stage + r * RAW_STAGE;
           mbar_expect_tx(raw_full + r, RAW_STAGE);
           tma_load_2d(dst, &map_a, raw_full + r, kb * KB, s.ft * TS_MT);
-          if (!TF32) tma_load_2d(dst + TS_RAW_BOX, &map_a, raw_full + r, kb * KB + 32, s.ft * TS_MT);
+          if (!TF32 && HALF != 2) tma_load_2d(dst + TS_RAW_BOX, &map_a, raw_full + r, kb * KB + 32, s.ft * TS_MT);
         }
       }
     }
@@ -240,6 +247,8 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
               umma_ts<true>(d_corr, a_hi, w_lo, dhi, idesc, first);  // hi*lo -> correction
               umma_ts<true>(d_corr, a_lo, w_hi, dhi, idesc, 1);      // lo*hi -> correction
               umma_ts<true>(d_main, a_hi, w_hi, dhi, idesc, first);  // hi*hi -> main
+            } else if (HALF) {
+              umma_ts<false>(d_main, a_hi, w_hi, dhi, idesc, first);
             } else {
               umma_ts<false>(d_main, a_hi, w_lo, dhi, idesc, first);
               umma_ts<false>(d_main, a_lo, w_hi, dhi, idesc, 1);
@@ -296,6 +305,35 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             tmem_st16(dst + 16 * h, hi);
             tmem_st16(dst + 32 + 16 * h, lo);
           }
+        } else if (HALF == 2) {
+          // the activations are stored as bf16: the row's 128 bytes ARE the operand (64 elements = 32 packed columns);
+          // only the PReLU prologue touches them (unpack, prelu, round back)
+          uint4 x[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 t = lds128f(raw + ((c ^ sw) << 4));
+            x[c] = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+          }
+          mbar_wait(a_empty + as, aph ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t hi[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t w4[4] = {x[4 * h + c].x, x[4 * h + c].y, x[4 * h + c].z, x[4 * h + c].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t w = w4[i];
+                if (pro) {
+                  const float e0 = prelu(__uint_as_float(w << 16), alpha_in), e1 = prelu(__uint_as_float(w & 0xffff0000u), alpha_in);
+                  w = cvt_bf16x2(e0, e1);
+                }
+                hi[4 * c + i] = w;
+              }
+            }
+            tmem_st16(dst + 16 * h, hi);
+          }
         } else {
           float4 x[2][8];  // the two 32-float boxes of the k-block
 #pragma unroll
@@ -323,7 +361,7 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
               lo[4 * c] = lv.x; lo[4 * c + 1] = lv.y; lo[4 * c + 2] = lv.z; lo[4 * c + 3] = lv.w;
             }
             tmem_st16(dst + 16 * h, hi);
-            tmem_st16(dst + 32 + 16 * h, lo);
+            if (!HALF) tmem_st16(dst + 32 + 16 * h, lo);  // (HALF = 1: the activations are rounded to one bf16 plane)
           }
         }
         mbar_arrive(raw_empty + r);  // the tile's values have been consumed by the conversions above
@@ -395,6 +433,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
               v[4 * i + 3] = fmaf(r, v[4 * i + 3], fmaf(-mur, k2.w, k1.w));
             }
           }
+          if (DBF) {  // the consumers (and the statistics) see the stored, rounded values
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+          }
           if (STATS && valid) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -430,7 +472,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             for (int t = 0; t < 4; ++t) {
               const int rr = 4 * (t0 + t) + rsub;
               if (RES) { val[t].x += rv[t].x; val[t].y += rv[t].y; val[t].z += rv[t].z; val[t].w += rv[t].w; }
-              if (fq + rr < a.F) stg128(a.D + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+              if (fq + rr < a.F) {
+                if (DBF) stg_bf16x4(reinterpret_cast<__nv_bfloat16*>(a.D) + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+                else stg128(a.D + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+              }
             }
           }
         } else {     // 4 lanes per row, 8 rows per instruction
@@ -449,7 +494,10 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           for (int t = 0; t < 4; ++t) {
             const int rr = 8 * t + rsub;
             if (RES) { val[t].x += rv[t].x; val[t].y += rv[t].y; val[t].z += rv[t].z; val[t].w += rv[t].w; }
-            if (fq + rr < a.F) stg128(a.D + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+            if (fq + rr < a.F) {
+              if (DBF) stg_bf16x4(reinterpret_cast<__nv_bfloat16*>(a.D) + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+              else stg128(a.D + (fq + rr) * O + s.c0 + j + c4 * 4, val[t]);
+            }
           }
         }
         __syncwarp();
@@ -540,7 +588,8 @@ static int env_int(const char* name, int dflt) {
 
 bool ts_gemm_eligible(const GemmArgs& a) {
   const int kb = a.tf32 ? 32 : 64;
-  return a.W_hi != nullptr && a.W_lo != nullptr && a.Kd % kb == 0 && a.O % 16 == 0 && a.F >= 1 &&
+  if (a.half && a.tf32) return false;
+  return a.W_hi != nullptr && (a.W_lo != nullptr || a.half) && a.Kd % kb == 0 && a.O % 16 == 0 && a.F >= 1 &&
          a.F < ((int64_t)1 << 31) - TS_MT && a.nred_z == nullptr;
 }
 
@@ -610,7 +659,8 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
   if (cl != 1 && cl != 2 && cl != 4) cl = 2;
   while (cl > 1 && ntiles < 2 * cl) cl >>= 1;
   const int nacc = tf32 ? 2 : 1;
-  const size_t raw_stage = tf32 ? TS_RAW_BOX : 2 * TS_RAW_BOX;
+  const int npl = g.half ? 1 : 2;
+  const size_t raw_stage = (tf32 || g.half == 2) ? TS_RAW_BOX : 2 * TS_RAW_BOX;
   const size_t fixed = TS_EPI_BYTES + 1024, budget = 227 * 1024;
   int nclusters = 0;
   size_t smem = 0;
@@ -636,11 +686,21 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     a.a_stages = (512 - a.nd * nacc * a.nmax) / TS_ACOLS;
     if (a.a_stages > TS_MAXST) a.a_stages = TS_MAXST;
     // shared memory: weight ring + raw activation ring + transposition buffers + barriers
-    const size_t w_stage = 2 * (size_t)a.nmax * 128;
-    a.raw_stages = tf32 ? 3 : 2;
+    const size_t w_stage = npl * (size_t)a.nmax * 128;
+    // raw ring depth 2: each converter group then owns one raw stage.  A 3-deep ring is sound on paper and ran clean in
+    // the TF32 flavour, but with bf16-stored activations (HALF = 2: 256-cycle k-blocks) it produced wrong tiles and
+    // eventually hangs at F = 102k (measured, scratch/run21.sh; 2-deep: bit-stable over repeated launches) — kept at 2
+    // for every flavour until that is understood.
+    a.raw_stages = 2;
     a.w_stages = (int)((budget - fixed - a.raw_stages * raw_stage) / w_stage);
     if (a.w_stages > TS_MAXST) a.w_stages = TS_MAXST;
     CTN_REQUIRE(a.w_stages >= 2, "ts_gemm: shared memory budget exceeded (nmax %d)", a.nmax);
+    {  // debug overrides of the ring depths
+      static const int wst = env_int("CTN_TS_WST", 0), rst = env_int("CTN_TS_RST", 0), ast = env_int("CTN_TS_AST", 0);
+      if (wst >= 2 && wst <= a.w_stages) a.w_stages = wst;
+      if (rst >= 2 && rst <= a.raw_stages) a.raw_stages = rst;
+      if (ast >= 2 && ast <= a.a_stages) a.a_stages = ast;
+    }
     smem = a.w_stages * w_stage + a.raw_stages * raw_stage + fixed;
     nclusters = want;
     if (cl == 1) break;
@@ -653,8 +713,8 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
   const int grid = nclusters * cl;
   CUtensorMap mh, ml, ma;
   CTN_TRY(make_map(&mh, g.W_hi, g.O, g.Kd, tf32, a.nmax / cl));
-  CTN_TRY(make_map(&ml, g.W_lo, g.O, g.Kd, tf32, a.nmax / cl));
-  CTN_TRY(make_map(&ma, g.A, g.F, g.Kd, true, TS_MT));
+  CTN_TRY(make_map(&ml, g.half ? g.W_hi : g.W_lo, g.O, g.Kd, tf32, a.nmax / cl));  // (unused in the single-plane mode)
+  CTN_TRY(make_map(&ma, g.A, g.F, g.Kd, g.half != 2, TS_MT));  // fp32 rows of 32 floats, or bf16 rows of 64 elements
 #define CTN_TS_LAUNCH(...)                                                                                       \
   do {                                                                                                           \
     static unsigned long long attr_mask = 0; /* the attributes are per device */                                 \
@@ -667,7 +727,16 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     }                                                                                                            \
     launch_clustered(ts_gemm_kernel<__VA_ARGS__>, grid, cl, smem, s, mh, ml, ma, a);                             \
   } while (0)
-  if (tf32) {
+  if (g.half) {  // reduced-precision inference: the combinations the model's forward issues
+    const bool dbf = g.d_bf16 != 0;
+    if (g.half == 1 && dbf && !fold && !res && stats) CTN_TS_LAUNCH(false, false, false, true, 1, true);
+    else if (g.half == 1 && dbf && !fold && !res && !stats) CTN_TS_LAUNCH(false, false, false, false, 1, true);
+    else if (g.half == 1 && !dbf && fold && !res && !stats) CTN_TS_LAUNCH(false, true, false, false, 1, false);
+    else if (g.half == 1 && !dbf && !fold && !res && !stats) CTN_TS_LAUNCH(false, false, false, false, 1, false);
+    else if (g.half == 2 && !dbf && fold && res && !stats) CTN_TS_LAUNCH(false, true, true, false, 2, false);
+    else if (g.half == 2 && !dbf && !fold && !res && !stats) CTN_TS_LAUNCH(false, false, false, false, 2, false);
+    else return -1;
+  } else if (tf32) {
     if (!fold && !res && !stats) CTN_TS_LAUNCH(true, false, false, false);
     else if (!fold && !res && stats) CTN_TS_LAUNCH(true, false, false, true);
     else if (fold && !res && !stats) CTN_TS_LAUNCH(true, true, false, false);
@@ -682,6 +751,7 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     else return -1;
   }
 #undef CTN_TS_LAUNCH
+  if (g.half) return check_launch(g.O > g.Kd ? "ts_gemm_kernel<bf16 x1> up" : "ts_gemm_kernel<bf16 x1> down");
   return check_launch(g.tf32 ? (g.O > g.Kd ? "ts_gemm_kernel<tf32> up" : "ts_gemm_kernel<tf32> down")
                              : (g.O > g.Kd ? "ts_gemm_kernel<bf16> up" : "ts_gemm_kernel<bf16> down"));
 }

@@ -62,6 +62,14 @@ static void timing_mark(const char* what) {
 int check_launch(const char* what) {
   __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   if (timing_enabled()) timing_mark(what);
+  static const int debug_launch = getenv("CTN_DEBUG_LAUNCH") != nullptr && getenv("CTN_DEBUG_LAUNCH")[0] == '1';
+  if (debug_launch) {  // debug: name every launch and wait for it (finds the kernel that faults or never ends)
+    fprintf(stderr, "[ctn] %s ...", what);
+    fflush(stderr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    fprintf(stderr, " %s\n", cudaGetErrorString(e));
+    fflush(stderr);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -75,11 +83,11 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t s);
 int run_encoder_fwd(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int run_encoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
-int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t);
+int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t, int bf16 = 0);
 int run_prep_normfold(const float*, const float*, const float*, int, int, int, int64_t, float*, float*, float*, int64_t,
                       int64_t, cudaStream_t);
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
-                   int, int, float*, double*, const float*, cudaStream_t);
+                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
@@ -159,6 +167,13 @@ int launch_gemm(const GemmArgs& a0, cudaStream_t s) {
   // frame-major kernel (gemm_ts.cu): any O % 16 == 0; channel-major kernel (gemm_tc.cu): O % 128 == 0.
   // CTN_GEMM_SS=1 (debug) never uses the frame-major kernel.
   static const bool use_ss = env_flag("CTN_GEMM_SS");
+  if (a0.half) {  // reduced-precision inference exists in the frame-major kernel only (bf16-stored operands / outputs)
+    CTN_REQUIRE(!force_simt() && ts_gemm_eligible(a0), "reduced-precision 1x1 conv: needs pre-split bf16 weight planes, "
+                "Kd %% 64 == 0 and O %% 16 == 0 (got Kd=%d O=%d)", a0.Kd, a0.O);
+    const int rc = launch_gemm_ts(a0, s);
+    CTN_REQUIRE(rc >= 0, "reduced-precision 1x1 conv: this prologue / epilogue combination is not built");
+    return rc;
+  }
   const bool off_grid = use_ss ? (a0.Kd % 64 != 0 || a0.O % 128 != 0 || a0.F < 16) : (a0.Kd % 64 != 0 || a0.O % 16 != 0);
   if (force_simt() || off_grid) return launch_gemm_simt(a0, s);
   static const bool simt_fwd = env_flag("CTN_SIMT_FWD"), simt_bwd = env_flag("CTN_SIMT_BWD");  // A/B debugging only
@@ -378,6 +393,7 @@ struct Ctx {
   const float* params;
   char* ws;
   cudaStream_t s;
+  int bf16_act = 0;           // reduced-precision inference: z1 / z2 stored as bf16, one bf16 plane per GEMM operand
   float* bn_state = nullptr;  // BN running statistics [nblk][rm1 H | rv1 H | rm2 H | rv2 H] (forward only)
   int bn_batch = 1;           // BN: 1 = batch statistics (+ running update), 0 = running statistics
   template <typename T>
@@ -426,6 +442,11 @@ struct Ctx {
 
 static int check_io(const ctn_config* cfg, int M, int T, const void* ws, int64_t ws_bytes, int training) {
   CTN_TRY(validate(cfg));
+  CTN_REQUIRE(training >= 0 && training <= 2, "mode must be 0 (inference), 1 (training) or 2 (bf16 inference)");
+  if (training == 2)
+    CTN_REQUIRE(cfg->N % 64 == 0 && cfg->B % 64 == 0 && cfg->H % 64 == 0 && cfg->norm_type != CTN_NORM_BN,
+                "bf16 inference needs N, B, H multiples of 64 and gLN / cLN (got N=%d B=%d H=%d norm=%d)", cfg->N, cfg->B,
+                cfg->H, cfg->norm_type);
   CTN_REQUIRE(M >= 1 && M <= 65535, "batch size M must be in [1, 65535] (got %d)", M);
   CTN_REQUIRE(T >= cfg->L, "input has %d samples, fewer than one frame (L=%d)", T, cfg->L);
   const int64_t need = ctn_workspace_bytes(cfg, M, T, training);
@@ -496,12 +517,14 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
   float* w = X.at<float>(p.w);
   CTN_TRY(run_encoder_fwd(mixture, X.params + L.U, M, p.T, c.N, c.L, w, s));
   CTN_TRY(run_row_stats(w, nullptr, F, c.N, X.at<float>(p.rowstat0), s));
+  const int half = X.bf16_act ? 1 : 0;  // reduced-precision inference: one bf16 plane per operand (gemm_ts.cu)
   {
     GemmArgs a = {};
     a.A = w; a.W = X.at<float>(p.Wbg); a.D = X.x(0); a.F = F; a.O = c.B; a.Kd = c.N; a.K = K;
     a.c1 = X.at<float>(p.c1b); a.c2 = X.at<float>(p.c2b);
     a.st.row = X.at<float>(p.rowstat0);
     a.W_hi = X.at<char>(p.pl_Wbg); a.W_lo = X.at<char>(p.pl_Wbg + p.pl_lo); a.tf32 = fwd_tf32;
+    a.half = half;
     CTN_TRY(launch_gemm(a, s));
   }
   for (int b = 0; b < nblk; ++b) {
@@ -513,13 +536,14 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.W_hi = X.at<char>(p.pl_W1) + (int64_t)b * c.H * c.B * esz;
       a.W_lo = X.at<char>(p.pl_W1 + p.pl_lo) + (int64_t)b * c.H * c.B * esz;
       a.tf32 = fwd_tf32;
+      a.half = half; a.d_bf16 = half;  // z1 stored as bf16
       CTN_TRY(launch_gemm(a, s));
     }
-    if (cln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s));
+    if (cln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s, half));
     if (bn) CTN_TRY(bn_forward(X, b, 0, X.z1(b)));
     CTN_TRY(run_dwconv_fwd(X.z1(b), X.blk(b, L.a1), X.stats(b, 0), X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K,
-                           c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s));
-    if (cln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s));
+                           c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s, half));
+    if (cln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s, half));
     if (bn) {  // statistics of prelu(z2) -> (s, t) -> this block's folded pointwise weight and its operand planes
       CTN_TRY(bn_forward(X, b, 1, X.z2(b)));
       float* W2g = X.at<float>(p.W2g) + (int64_t)b * c.B * c.H;
@@ -542,6 +566,7 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.W_hi = X.at<char>(p.pl_W2g) + (int64_t)b * c.B * c.H * esz;
       a.W_lo = X.at<char>(p.pl_W2g + p.pl_lo) + (int64_t)b * c.B * c.H * esz;
       a.tf32 = fwd_tf32;
+      a.half = half ? 2 : 0;  // z2 is stored as bf16
       CTN_TRY(launch_gemm(a, s));
     }
   }
@@ -549,6 +574,7 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
     GemmArgs a = {};
     a.A = X.x(nblk); a.W = X.params + L.Wm; a.D = X.at<float>(p.score); a.F = F; a.O = c.C * c.N; a.Kd = c.B; a.K = K;
     a.W_hi = X.at<char>(p.pl_Wm); a.W_lo = X.at<char>(p.pl_Wm + p.pl_lo); a.tf32 = fwd_tf32;
+    a.half = half;
     CTN_TRY(launch_gemm(a, s));
   }
   return run_decoder_fwd(X.at<float>(p.score), w, X.params + L.V, M, K, c.C, c.N, c.L, p.T,
@@ -800,7 +826,7 @@ int32_t ctn_num_frames(const ctn_config* cfg, int32_t T) {
 
 int64_t ctn_workspace_bytes(const ctn_config* cfg, int32_t M, int32_t T, int32_t training) {
   if (validate(cfg) || M < 1 || T < cfg->L) return -1;
-  return make_plan(*cfg, M, T, training).total;
+  return make_plan(*cfg, M, T, training == 1 ? 1 : 0).total;  // (mode 2, bf16 inference, uses the inference plan)
 }
 
 int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const float* mixture, int32_t M, int32_t T,
@@ -809,7 +835,9 @@ int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const floa
   CTN_REQUIRE(params && mixture && est, "model_forward: null pointer");
   CTN_REQUIRE(cfg->norm_type != CTN_NORM_BN, "model_forward: norm_type BN carries running statistics, call "
               "ctn_model_forward_bn");
-  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, training), params, reinterpret_cast<char*>(workspace), stream};
+  Ctx X = {*cfg, make_layout(*cfg), make_plan(*cfg, M, T, training == 1 ? 1 : 0), params, reinterpret_cast<char*>(workspace),
+           stream};
+  X.bf16_act = training == 2 ? 1 : 0;
   return model_forward(X, mixture, est);
 }
 

@@ -281,6 +281,11 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// four floats -> four bf16 (round to nearest even), one 8-byte store
+__device__ __forceinline__ void stg_bf16x4(__nv_bfloat16* dst, const float4& v) {
+  const uint32_t lo = cvt_bf16x2(v.x, v.y), hi = cvt_bf16x2(v.z, v.w);
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void stg128(float* dst, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

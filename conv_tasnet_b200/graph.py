@@ -206,7 +206,7 @@ class GraphedInference:
         self._cap = collections.OrderedDict()  # shape -> (graph, static input, static output, workspace)
 
     def __call__(self, mixture):
-        key = tuple(mixture.shape)
+        key = (tuple(mixture.shape), str(getattr(getattr(self.model, "module", self.model), "inference_dtype", None)))
         entry = self._cap.get(key)
         if entry is None:
             while len(self._cap) >= max(1, self.max_shapes):

@@ -54,14 +54,19 @@ int64_t ctn_param_floats(const ctn_config* cfg);
 int32_t ctn_param_layout(const ctn_config* cfg, int64_t* offsets, int64_t* numels, int32_t n);
 /* frames K for T samples (Encoder, src/conv_tasnet.py:113) */
 int32_t ctn_num_frames(const ctn_config* cfg, int32_t T);
-/* bytes of scratch the model calls need; `training` != 0 keeps the activation stash for backward */
+/* bytes of scratch the model calls need; `training` == 1 keeps the activation stash for backward (0 and 2: inference) */
 int64_t ctn_workspace_bytes(const ctn_config* cfg, int32_t M, int32_t T, int32_t training);
 
 /* ---- whole-path entry points ------------------------------------------------------------ */
 /* ConvTasNet.forward (src/conv_tasnet.py:45-60): mixture [M,T] -> est [M,C,T] (right zero-padded).
  * training != 0 additionally leaves the stash in `workspace` for ctn_model_backward and runs the 1x1 convs with the
  * TF32x3 operand split (fp32-class forward: needed for gradient parity); training == 0 uses the bf16x3
- * split (outputs within 2e-5 of the training path, budget 1e-4). */
+ * split (outputs within 2e-5 of the training path, budget 1e-4).
+ * training == 2: reduced-precision inference ("bf16 forward", BASELINE configs[2]; the reference has no such path —
+ * src/utils.py:40, src/pit_criterion.py:72 — so the budget is the north star's 2e-2 against the fp32 result): the two
+ * H-wide activations of every TemporalBlock (z1, z2) are STORED as bf16 and every 1x1 conv runs one bf16 x bf16 MMA per
+ * k-step with fp32 accumulation (frame-major tcgen05 kernel); the B-wide residual stream, the normalisation statistics,
+ * the encoder / decoder and all I/O stay fp32.  Needs N, B, H multiples of 64 and gLN or cLN. */
 int32_t ctn_model_forward(const ctn_config* cfg, const float* params, const float* mixture,
                           int32_t M, int32_t T, float* est, void* workspace, int64_t workspace_bytes,
                           int32_t training, cudaStream_t stream);
@@ -171,10 +176,12 @@ int32_t ctn_conv1x1(const float* A, const float* W, int32_t w_is_kn, float* D, i
                     const double* gln_acc, const float* rowstat, const float* res, double* stat_out,
                     const float* alpha_out, cudaStream_t stream);
 /* The same 1x1 convolution with the weight operand already split into the planes the tensor-core kernels read
- * ([O, Kd] row-major; tf32 = 1: fp32 planes hi = tf32(W), lo = W - hi; tf32 = 0: bf16 planes hi = bf16(W), lo = bf16(W - hi)),
- * as the whole-model path holds them (one split per step instead of one per call).  No prologue / epilogue.
+ * ([O, Kd] row-major), as the whole-model path holds them (one split per step instead of one per call).  No prologue /
+ * epilogue.  mode: 0 = bf16x3 (bf16 planes hi = bf16(W), lo = bf16(W - hi)); 1 = TF32x3 (fp32 planes hi = tf32(W),
+ * lo = W - hi); 2..4 = the single-bf16 MMA of the reduced-precision inference path (W_hi bf16 only, W_lo unused):
+ * 2 = A fp32 -> D fp32, 3 = A fp32 -> D stored as bf16, 4 = A stored as bf16 -> D fp32.
  * Replaces nn.Conv1d(kernel_size=1, bias=False) calls, src/conv_tasnet.py:223,262,191. */
-int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t tf32, float* D, int64_t F,
+int32_t ctn_conv1x1_planes(const float* A, const void* W_hi, const void* W_lo, int32_t mode, float* D, int64_t F,
                            int32_t O, int32_t Kd, int32_t K, cudaStream_t stream);
 
 /* weight gradient: dW[O,I] += sum_f G[f,o] * act(f,i), act = Act or gamma*(prelu(Act,alpha)-mu)*r+beta when

@@ -423,3 +423,30 @@ def test_dwconv_bwd_with_fused_gln_apply_equals_the_two_pass_schedule(causal, Pk
     assert rel_err(dg_b.cpu(), dg_a.cpu()) < 1e-5 and rel_err(db_b.cpu(), db_a.cpu()) < 1e-5
     assert rel_err(red_b.cpu(), red_a.cpu()) < 1e-6
     assert abs(dal_b.item() - dal_a.item()) < 1e-4 * max(1.0, abs(dal_a.item()))
+
+
+@pytest.mark.parametrize("F", [130, 9597, 51184])
+@pytest.mark.parametrize("mode,Kd,Ochan", [(0, 256, 512), (0, 512, 256), (1, 256, 512), (2, 256, 256), (3, 256, 512),
+                                           (4, 512, 256), (4, 256, 512), (0, 64, 48)])
+def test_conv1x1_planes_every_operand_flavour(F, mode, Kd, Ochan):
+    """ctn_conv1x1_planes: pre-split weight planes, every operand flavour of the tcgen05 kernels — 0 bf16x3, 1 TF32x3,
+    2..4 the single-bf16 MMA of the reduced-precision inference path (fp32 / bf16-stored activations in, fp32 / bf16
+    out) — at one, a few and many frame tiles per SM (the persistent kernel's segment loop), 5 launches each.
+    Expected value: the same product in fp64 from the operands as the flavour rounds them."""
+    A, W = rnd(F, Kd, seed=41), rnd(Ochan, Kd, seed=42, scale=1 / 16)
+    if mode == 1:
+        hi = (W.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)  # round to nearest tf32 (ties away)
+        lo = W - hi
+    else:
+        hi = W.to(torch.bfloat16)
+        lo = (W - hi.float()).to(torch.bfloat16)
+    a_in = A.to(torch.bfloat16) if mode == 4 else A
+    D = torch.empty(F, Ochan, device=dev(), dtype=torch.bfloat16 if mode == 3 else torch.float32)
+    a_ref = A if mode < 2 else A.to(torch.bfloat16).float()
+    w_ref = W if mode < 2 else hi.float()
+    want = a_ref.double() @ w_ref.double().t()
+    tol = 4e-3 if mode == 3 else TOL_TC  # mode 3 stores bf16: 2^-9 per element
+    for _ in range(5):
+        D.zero_()
+        call("ctn_conv1x1_planes", P(a_in), P(hi), P(lo), mode, P(D), F, Ochan, Kd, 3199)
+        assert rel_err(D.float().cpu(), want.cpu()) < tol

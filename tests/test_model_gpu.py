@@ -660,3 +660,54 @@ def test_sharded_separator_matches_plain_forward_on_ragged_utterances():
             s, e, m = srcs[i].double().numpy(), reordered[0].cpu().double().numpy(), mixes[i].double().numpy()
             want.append(np.mean([O.cal_SISNR_np(s[c], e[c]) - O.cal_SISNR_np(s[c], m) for c in range(cfgd["C"])]))
     assert abs(tot / len(lens) - float(np.mean(want))) < 1e-2
+
+
+@pytest.mark.parametrize("norm,causal,M,T", [("cLN", True, 2, 12000), ("gLN", False, 3, 32000), ("cLN", True, 32, 32000)])
+def test_bf16_inference_mode_stays_within_the_reduced_precision_budget(norm, causal, M, T):
+    """BASELINE configs[2] ("bf16 forward"; the last case is its full size: causal cLN, 32 x 4 s).  The reference has no
+    reduced-precision path (src/utils.py:40, src/pit_criterion.py:72 are fp32-only), so the yardstick is the north
+    star's: outputs within max-rel-err 2e-2 of the fp32 result and SI-SNR within 0.01 dB.  The fp32 result here is the
+    fp32 forward of the same weights (itself within 1e-4 of the oracle by the tests above)."""
+    from conv_tasnet_b200 import ConvTasNet, cal_loss
+    cfg = O.Config(**{**O.PAPER.as_dict(), "norm_type": norm, "causal": causal})
+    model = ConvTasNet(**cfg.as_dict())
+    model.load_state_dict(O.init_state_dict(cfg, seed=0))
+    model = model.cuda().eval()
+    mix, src, lens = O.synthetic_batch(M, T, cfg.C, cfg.L, 77)
+    mix, src = mix.cuda(), src.cuda()
+    with torch.no_grad():
+        ref = model(mix)
+        model.half_inference(True)
+        got = model(mix)
+        assert model.inference_dtype == torch.bfloat16
+        model.half_inference(False)
+        again = model(mix)
+    assert torch.equal(again, ref)                       # the fp32 path is untouched by the toggle
+    assert not torch.equal(got, ref)                     # ... and the bf16 path is a different computation
+    err = ((got - ref).abs().amax(dim=(1, 2)) / ref.abs().amax(dim=(1, 2))).max().item()
+    assert err < 2e-2, err
+    # SI-SNR within 0.01 dB.  With random-init weights the estimate is ~40 dB away from the sources: the projection onto
+    # the source that SI-SNR is built on is ~1e-2 of the signal, so a 1e-3 perturbation moves it by a tenth of a dB — the
+    # criterion is only well conditioned in the regime it is meant for, an estimate that resembles its target.  Checked
+    # there: targets = the fp32 estimate + noise at the paper's operating point (SI-SNR ~ 15 dB, Luo & Mesgarani Table 2;
+    # the bf16 path's error, ~0.4 % rms, adds in quadrature to that noise), and bounded loosely (0.2 dB) on the raw
+    # random-init sources.
+    g = torch.Generator().manual_seed(5)
+    target = ref + 0.178 * ref.pow(2).mean().sqrt() * torch.randn(ref.shape, generator=g).cuda()
+    with torch.no_grad():
+        _, snr_ref, _, _ = cal_loss(target, ref.clone(), lens)
+        _, snr_got, _, _ = cal_loss(target, got.clone(), lens)
+        assert 12.0 < snr_ref.min().item() and snr_ref.max().item() < 18.0, (snr_ref.min().item(), snr_ref.max().item())
+        assert (snr_ref - snr_got).abs().max().item() < 0.01, (snr_ref - snr_got).abs().max().item()
+        _, raw_ref, _, _ = cal_loss(src, ref.clone(), lens)
+        _, raw_got, _, _ = cal_loss(src, got.clone(), lens)
+        assert (raw_ref - raw_got).abs().max().item() < 0.2, (raw_ref - raw_got).abs().max().item()
+    # training is unaffected: under autograd the forward is the fp32-class one whatever inference_dtype says
+    model.half_inference(True).train()
+    est = model(mix[:1, :8000])
+    model.eval()
+    with torch.no_grad():
+        model.half_inference(False)
+        assert rel_err(est.detach().cpu(), model(mix[:1, :8000]).cpu()) < 1e-4
+    with pytest.raises(ValueError):
+        ConvTasNet(32, 8, 16, 32, 3, 2, 1, 2).cuda().half_inference(True)
