@@ -506,7 +506,9 @@ def main():
         step_bytes = frames * (e_fwd + e_bwd + 5 * C_ * S_) * 4 + 10 * 4 * n_params * world
     else:
         step_flops = frames * 2 * mac_fwd
-        step_bytes = frames * (e_fwd + (2 * C_ * S_ if mode == "fwd_loss" else 0)) * 4 + 4 * n_params * world
+        esz = 2 if dtype == "bf16" else 4  # SURVEY §8d counts the bf16 config at 2 bytes per element (a LOWER bound on the
+        # bytes this path moves: it keeps the residual stream, the encoder / decoder and all I/O in fp32)
+        step_bytes = frames * (e_fwd + (2 * C_ * S_ if mode == "fwd_loss" else 0)) * esz + 4 * n_params * world
     t_step = secs / args.steps
 
     line = {"metric": METRIC[mode], "value": value, "unit": "audio-s/s",

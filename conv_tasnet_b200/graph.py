@@ -136,12 +136,18 @@ class GraphedTrainStep:
             for p, v in zip(m.parameters(), m.grad_views()):
                 p.grad = v
         graphs = []
+        # uneven shards: this rank's loss gradient is weighted by world * M_local / M_global (data_parallel.py); the shard
+        # sizes of a captured shape are fixed, so the factor is formed once, eagerly (one 4-byte all-reduce), and baked in
+        if getattr(dp, "weight_by_batch", False):
+            one = dp.grad_scale_for(mix.shape[0], mix.device).to(torch.float32).clone()
+        else:
+            one = torch.ones(1, dtype=torch.float32, device=mix.device)
+        torch.cuda.synchronize(mix.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, pool=pool):
             est, ws, token = m._run_forward(mix, training=True)
             loss, _max_snr, _idx, coef, _ = _pit_forward_raw(src, est, lens, False)
             d_est = torch.empty_like(est)
-            one = torch.ones(1, dtype=torch.float32, device=est.device)
             B, C, T = src.shape
             _lib.check(L.ctn_pit_backward(_lib.ptr(src), _lib.ptr(est), _lib.ptr(lens), _lib.ptr(coef), _lib.ptr(one),
                                           B, C, T, _lib.ptr(d_est), _lib.stream()))

@@ -72,9 +72,42 @@ def _worker(rank, world, port, q):
     opt2 = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
     step = GraphedTrainStep(dp, opt2, warmup=0)
     losses_g = [step(m.contiguous(), s.contiguous(), l.contiguous()).item() for _ in range(3)]
-    assert step.captured and step._stage_graphs is not None and len(step._stage_graphs) == cfgd["R"] + 2
+    cap = next(iter(step._cap.values()))
+    assert step.captured and cap.stage_graphs is not None and len(cap.stage_graphs) == cfgd["R"] + 2
     assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-4, (losses_e, losses_g)
     assert ((model.flat_params - p_eager).abs().max() / p_eager.abs().max()).item() < 1e-5
+    # uneven shards (the reference's batches vary in size, src/data.py:84-108): 5 items over 2 ranks = 3 + 2; the
+    # data-parallel gradient must still be the gradient of the mean over the GLOBAL batch — eager and graph-replayed
+    model.load_state_dict(sd0)
+    mix5, src5, lens5 = O.synthetic_batch(5, 4000, 2, 20, 12)
+    mix5, src5, lens5 = mix5.cuda(), src5.cuda(), lens5.cuda()
+    m5, s5, l5 = (t.contiguous() for t in shard_batch(rank, world, mix5, src5, lens5))
+    assert m5.shape[0] == (3 if rank == 0 else 2)
+    for p in model.parameters():
+        p.grad = None
+    est = dp(m5)
+    loss, *_ = cal_loss(s5, est, l5)
+    loss.backward()
+    torch.cuda.synchronize()
+    g_uneven = model.flat_grads.clone()
+    single = ConvTasNet(**cfgd).cuda().train()
+    single.load_state_dict(model.state_dict())
+    est = single(mix5)
+    loss_full, *_ = cal_loss(src5, est, lens5)
+    loss_full.backward()
+    torch.cuda.synchronize()
+    err5 = ((g_uneven - single.flat_grads).norm() / single.flat_grads.norm()).item()
+    assert err5 < 1e-4, err5
+    opt3 = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
+    opt_s = FusedAdam(single, lr=1e-3, max_grad_norm=5.0)
+    step5 = GraphedTrainStep(dp, opt3)
+    step5(m5, s5, l5)
+    est = single(mix5)
+    loss_full, *_ = cal_loss(src5, est, lens5)
+    opt_s.zero_grad()
+    loss_full.backward()
+    opt_s.step()
+    assert ((model.flat_params - single.flat_params).abs().max() / single.flat_params.abs().max()).item() < 1e-4
     dist.barrier()
     dist.destroy_process_group()
 
