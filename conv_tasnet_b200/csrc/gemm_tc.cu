@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
   float2* s_wst = reinterpret_cast<float2*>(tail + 128);  // [WG_STAT_CACHE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TR(0);
   const int o0 = blockIdx.x * BM, i0 = blockIdx.y * NI;
   const int64_t fb = (int64_t)blockIdx.z * a.f_chunk;
   const int64_t fe = fb + a.f_chunk < a.F ? fb + a.f_chunk : a.F;
@@ -544,6 +545,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global data is touched only below
+  if (threadIdx.x == 0) TR(1);
 
   if (nkb > 0) {
     if (warp == 1) {
@@ -553,6 +555,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
           const int s = kb % WSTAGES, ph = (kb / WSTAGES) & 1;
           mbar_wait(full + s, ph);
           tc_fence_after();
+          if (kb < 16) TR(8 + kb);
           const uint32_t sb = smem_base + s * STAGE;
           const uint32_t g_hi = sb, g_lo = sb + A_PLANE, x_hi = sb + 2 * A_PLANE, x_lo = x_hi + B_PLANE;
 #pragma unroll
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
           umma_commit(empty + s);
         }
         umma_commit(tmem_full);
+        TR(2);
       }
     } else if (warp >= 4) {
       const int t = threadIdx.x - 128;
@@ -669,6 +673,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
       // ---- epilogue: add the partial tile to dW with TMA reductions ----
       mbar_wait(tmem_full, 0);
       tc_fence_after();
+      if (t == 0) TR(3);
       // TMEM gives lane = output row o, registers = columns i.  The tile is staged in shared memory (the operand stages
       // are free: every MMA has completed) as NI/32 boxes of [128 rows x 128 bytes] in the 128-byte-swizzle layout
       // (conflict-free 16-byte stores down a column), and one thread hands each box to the TMA engine as a bulk
@@ -695,12 +700,14 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
         }
         fence_proxy_async();  // the generic-proxy stores above must be visible to the TMA engine (async proxy)
         asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
+        if (t == 0) TR(6);
         if (warp == 4 && lane == 0) {
 #pragma unroll 1
           for (int b = 0; b < NI / 32; ++b)
             tma_reduce_add_2d(&map_dw, smem + b * (BM * 128), i0 + 32 * b, o0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may go once the engine has read it
+          TR(4);
         }
       }
 #else
@@ -733,6 +740,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<256>(tmem_base);
+  if (threadIdx.x == 0) TR(5);
 }
 
 // ------------------------------------------------------------------------------------------------
