@@ -33,6 +33,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -623,10 +625,21 @@ static void launch_clustered(void (*kernel)(KArgs...), int grid, int cl, size_t 
   timing_note_stream(stream);
 }
 
-// clusters of `cl` CTAs with `smem` bytes each that the device can hold at once (cached per kernel x cl x device)
-template <typename K>
-static int max_clusters(K kernel, int cl, size_t smem) {
+// clusters of `cl` CTAs with `smem` bytes each that the device can hold at once (every flavour has the same block size
+// and register bound, so one instantiation answers for all); cached per (device, cl, shared-memory size)
+static int max_clusters(int cl, size_t smem) {
   if (cl == 1) return sm_count();
+  struct Entry { int dev, cl; size_t smem; int n; };
+  static Entry cache[32];
+  static int ncache = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].dev == dev && cache[i].cl == cl && cache[i].smem == smem) return cache[i].n;
+  auto kernel = ts_gemm_kernel<false, false, false, false>;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sm_count() / cl * cl);
   cfg.blockDim = dim3(TS_THREADS);
@@ -641,9 +654,11 @@ static int max_clusters(K kernel, int cl, size_t smem) {
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
-    return 0;
+    n = 0;
   }
-  return n < sm_count() / cl ? n : sm_count() / cl;
+  if (n > sm_count() / cl) n = sm_count() / cl;
+  if (ncache < 32) cache[ncache++] = Entry{dev, cl, smem, n};
+  return n;
 }
 
 int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
@@ -704,7 +719,7 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     smem = a.w_stages * w_stage + a.raw_stages * raw_stage + fixed;
     nclusters = want;
     if (cl == 1) break;
-    const int fit = max_clusters(ts_gemm_kernel<false, false, false, false>, cl, smem);
+    const int fit = max_clusters(cl, smem);
     if (fit >= 1) {
       if (nclusters > fit) nclusters = fit;
       break;
