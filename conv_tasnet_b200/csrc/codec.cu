@@ -1,8 +1,8 @@
 // codec.cu — the two ends of the network: Encoder (framing conv + ReLU, src/conv_tasnet.py:108-121) and Decoder (mask
 // nonlinearity, mask * mixture_w, basis Linear(N, L), overlap_and_add, zero pad to T; src/conv_tasnet.py:131-146,57-59),
 // forward and backward.  These are skinny GEMMs (L = 20 outputs / reduction steps) around HBM-bound tensors; they run on
-// the CUDA cores.  All four kernels are templated on the frame length (LT = L for the paper's 20, else LT = 32 with
-// run-time guards) so the per-frame loops unroll without predicated-off instructions, keep several independent global
+// the CUDA cores.  All four kernels are templated on the frame length (LT = L for the paper's 20, else LT = 32 or 64 —
+// the paper's L = 40 — with run-time guards) so the per-frame loops unroll without predicated-off instructions, keep several independent global
 // loads in flight per thread, and pick their frame tile per launch so the grid fills whole waves of the SMs.
 #include "common.cuh"
 
@@ -10,7 +10,7 @@ namespace ctn {
 namespace {
 
 constexpr int MAXC = 4;
-constexpr int MAXL = 32;
+constexpr int MAXL = 64;
 
 int sm_count() {
   static int n = 0;
@@ -232,26 +232,31 @@ __global__ void __launch_bounds__(256) decoder_fwd_kernel(const float* __restric
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       if (c < C) {
-        float p[32];
 #pragma unroll
-        for (int l = 0; l < 32; ++l) p[l] = 0.f;
+        for (int lb = 0; lb < LT; lb += 32) {  // 32 outputs per transpose-reduce (two rounds for 32 < L <= 64)
+          if (lb < L) {
+            float p[32];
 #pragma unroll
-        for (int l = 0; l < LT; ++l) {
-          if (l < L) {
+            for (int l = 0; l < 32; ++l) p[l] = 0.f;
 #pragma unroll
-            for (int i4 = 0; i4 < NIT / 4; ++i4) {
-              if (i4 < ni4) {
-                const float4 v = Vt[(l * ni4 + i4) * 32 + lane];
-                p[l] = fmaf(sc[c][4 * i4 + 0], v.x, p[l]);
-                p[l] = fmaf(sc[c][4 * i4 + 1], v.y, p[l]);
-                p[l] = fmaf(sc[c][4 * i4 + 2], v.z, p[l]);
-                p[l] = fmaf(sc[c][4 * i4 + 3], v.w, p[l]);
+            for (int l = 0; l < 32; ++l) {
+              if (lb + l < LT && lb + l < L) {
+#pragma unroll
+                for (int i4 = 0; i4 < NIT / 4; ++i4) {
+                  if (i4 < ni4) {
+                    const float4 v = Vt[((lb + l) * ni4 + i4) * 32 + lane];
+                    p[l] = fmaf(sc[c][4 * i4 + 0], v.x, p[l]);
+                    p[l] = fmaf(sc[c][4 * i4 + 1], v.y, p[l]);
+                    p[l] = fmaf(sc[c][4 * i4 + 2], v.z, p[l]);
+                    p[l] = fmaf(sc[c][4 * i4 + 3], v.w, p[l]);
+                  }
+                }
               }
             }
+            const float tot = transpose_reduce32(p, lane);
+            if (lb + lane < L) out[c * L + lb + lane] = tot;
           }
         }
-        const float tot = transpose_reduce32(p, lane);
-        if (lane < L) out[c * L + lane] = tot;
       }
     }
   }
@@ -393,7 +398,7 @@ int run_encoder_fwd(const float* mix, const float* U, int M, int T, int N, int L
   CTN_REQUIRE(L >= 2 && T >= L, "encoder: need L >= 2 and T >= L (T=%d L=%d)", T, L);
   CTN_REQUIRE(L <= MAXL, "encoder: L <= %d supported (got %d)", MAXL, L);
   const int S = L / 2, K = (T - L) / S + 1;
-  auto kern = L == 20 ? encoder_fwd_kernel<20> : encoder_fwd_kernel<32>;
+  auto kern = L == 20 ? encoder_fwd_kernel<20> : L <= 32 ? encoder_fwd_kernel<32> : encoder_fwd_kernel<64>;
   const int tk = pick_tile(K, M, 0, 16, 64, slots_for(kern, 256, (size_t)(64 * S + L) * 4), 2);
   const size_t smem = (size_t)(tk * S + L) * sizeof(float);
   launch_kernel(kern, dim3(cdiv(K, tk), M), 256, smem, s, mix, U, T, K, N, L, tk, w);
@@ -404,7 +409,8 @@ int run_encoder_bwd(const float* mix, const float* w, const float* dwa, const fl
                     float* dU, cudaStream_t s) {
   const int S = L / 2, K = (T - L) / S + 1;
   CTN_REQUIRE(L <= MAXL, "encoder: L <= %d supported (got %d)", MAXL, L);
-  auto kern = L == 20 ? encoder_bwd_kernel<20> : encoder_bwd_kernel<32>;
+  auto kern = L == 20 ? encoder_bwd_kernel<20> : L <= 32 ? encoder_bwd_kernel<32> : encoder_bwd_kernel<64>;
+  CTN_TRY(ensure_smem((const void*)kern, (size_t)(64 * S + L + 256 * L) * 4));
   const int tk = pick_tile(K, M, 0, 32, 64, slots_for(kern, 256, (size_t)(64 * S + L + 256 * L) * 4), 4);
   const size_t smem = (size_t)(tk * S + L + 256 * L) * sizeof(float);
   launch_kernel(kern, dim3(cdiv(K, tk), M), 256, smem, s, mix, w, dwa, dwb, T, K, N, L, tk, dU);
@@ -419,8 +425,8 @@ int run_decoder_fwd(const float* score, const float* w, const float* V, int M, i
   const int S = L / 2, halo = (L - 1) / S;
   const int ni4 = (((N + 31) >> 5) + 3) >> 2;
   void (*kern)(const float*, const float*, const float*, int, int, int, int, int, int, int, float*);
-  if (N <= 256) kern = L == 20 ? decoder_fwd_kernel<20, 8> : decoder_fwd_kernel<32, 8>;
-  else kern = L == 20 ? decoder_fwd_kernel<20, 16> : decoder_fwd_kernel<32, 16>;
+  if (N <= 256) kern = L == 20 ? decoder_fwd_kernel<20, 8> : L <= 32 ? decoder_fwd_kernel<32, 8> : decoder_fwd_kernel<64, 8>;
+  else kern = L == 20 ? decoder_fwd_kernel<20, 16> : L <= 32 ? decoder_fwd_kernel<32, 16> : decoder_fwd_kernel<64, 16>;
   const size_t vbytes = (size_t)L * ni4 * 128 * 4;
   const size_t smem_hi = vbytes + (size_t)(32 + halo) * C * L * 4;
   CTN_TRY(ensure_smem((const void*)kern, smem_hi));
@@ -434,7 +440,7 @@ int run_decoder_bwd(const float* d_est, const float* score, const float* w, cons
                     int L, int T, int softmax, float* d_score, float* d_w, float* dV, cudaStream_t s) {
   CTN_REQUIRE(C >= 1 && C <= MAXC, "decoder: C must be in [1,%d] (got %d)", MAXC, C);
   CTN_REQUIRE(L <= MAXL, "decoder: L <= %d supported (got %d)", MAXL, L);
-  auto kern = L == 20 ? decoder_bwd_kernel<20> : decoder_bwd_kernel<32>;
+  auto kern = L == 20 ? decoder_bwd_kernel<20> : L <= 32 ? decoder_bwd_kernel<32> : decoder_bwd_kernel<64>;
   const size_t smem_hi = (size_t)(64 * C * L) * sizeof(float);
   CTN_TRY(ensure_smem((const void*)kern, smem_hi));
   const int tk = pick_tile(K, M, 0, 32, 64, slots_for(kern, 256, smem_hi), 2);

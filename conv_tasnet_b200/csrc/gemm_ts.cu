@@ -702,19 +702,25 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     if (a.a_stages > TS_MAXST) a.a_stages = TS_MAXST;
     // shared memory: weight ring + raw activation ring + transposition buffers + barriers
     const size_t w_stage = npl * (size_t)a.nmax * 128;
-    // raw ring depth 2: each converter group then owns one raw stage.  A 3-deep ring is sound on paper and ran clean in
-    // the TF32 flavour, but with bf16-stored activations (HALF = 2: 256-cycle k-blocks) it produced wrong tiles and
-    // eventually hangs at F = 102k (measured, scratch/run21.sh; 2-deep: bit-stable over repeated launches) — kept at 2
-    // for every flavour until that is understood.
+    // Ring depths of the rings the CONVERTERS wait on (raw tiles, TMEM A stages) must be EVEN: the two converter groups
+    // take k-blocks alternately, so with an odd depth a stage alternates between the groups and each group only observes
+    // every other phase of the stage's barrier — always with the same parity.  mbarrier.try_wait.parity then cannot tell
+    // "my phase completed" from "the phase two before it completed": a group that runs two uses ahead reads a tile
+    // that has not landed (or overwrites an operand the MMAs have not read) and arrives in the wrong phase.  Seen with a
+    // 3-deep raw ring and bf16-stored activations (256-cycle k-blocks: wrong tiles, then hangs / launch failures at
+    // F = 102k, scratch/run21.sh); latent for a 3-deep A ring.  With even depths a stage belongs to one group, which sees
+    // every phase.  (The weight ring and the accumulators are waited on by single threads / all epilogue warps.)
     a.raw_stages = 2;
+    a.a_stages &= ~1;
+    CTN_REQUIRE(a.a_stages >= 2, "ts_gemm: no room for two operand stages in tensor memory (nmax %d)", a.nmax);
     a.w_stages = (int)((budget - fixed - a.raw_stages * raw_stage) / w_stage);
     if (a.w_stages > TS_MAXST) a.w_stages = TS_MAXST;
     CTN_REQUIRE(a.w_stages >= 2, "ts_gemm: shared memory budget exceeded (nmax %d)", a.nmax);
     {  // debug overrides of the ring depths
       static const int wst = env_int("CTN_TS_WST", 0), rst = env_int("CTN_TS_RST", 0), ast = env_int("CTN_TS_AST", 0);
       if (wst >= 2 && wst <= a.w_stages) a.w_stages = wst;
-      if (rst >= 2 && rst <= a.raw_stages) a.raw_stages = rst;
-      if (ast >= 2 && ast <= a.a_stages) a.a_stages = ast;
+      if (rst >= 2 && rst <= a.raw_stages) a.raw_stages = rst & ~1;
+      if (ast >= 2 && ast <= a.a_stages) a.a_stages = ast & ~1;
     }
     smem = a.w_stages * w_stage + a.raw_stages * raw_stage + fixed;
     nclusters = want;

@@ -283,7 +283,7 @@ static int validate(const ctn_config* c) {
   CTN_REQUIRE(c->C <= 4, "config: C <= 4 supported (got %d)", c->C);
   CTN_REQUIRE(c->P <= 8, "config: P <= 8 supported (got %d)", c->P);
   CTN_REQUIRE(c->X <= 20, "config: X <= 20 (dilation 2^x)");
-  CTN_REQUIRE(c->L <= 32 && c->N <= 512, "config: L <= 32 and N <= 512 supported (got L=%d N=%d)", c->L, c->N);
+  CTN_REQUIRE(c->L <= 64 && c->N <= 512, "config: L <= 64 and N <= 512 supported (got L=%d N=%d)", c->L, c->N);
   CTN_REQUIRE(c->norm_type == CTN_NORM_GLN || c->norm_type == CTN_NORM_CLN || c->norm_type == CTN_NORM_BN,
               "config: norm_type must be 0 (gLN), 1 (cLN) or 2 (BN)");
   CTN_REQUIRE(c->causal || (c->P % 2 == 1), "config: non-causal needs odd P");

@@ -71,6 +71,17 @@ class ShardedDataParallel(nn.Module):
         else:
             self._drain()
 
+    def _on_stages(self, model, lo, hi):
+        """all-reduce the gradient slices of backward stages [lo, hi) as ONE contiguous slice (the buckets of consecutive
+        stages are adjacent in the flat buffer, in descending order) — used by graph.GraphedTrainStep"""
+        spans = [model.grad_bucket(s) for s in range(lo, hi)]
+        start = min(o for o, _ in spans)
+        end = max(o + c for o, c in spans)
+        assert sum(c for _, c in spans) == end - start, "stage buckets are not contiguous"
+        self._reduce(model.flat_grads[start:end])
+        if not self.overlap:
+            self._drain()
+
     def _reduce(self, view):
         avg = _has_avg(view, self.process_group)
         work = dist.all_reduce(view, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.process_group,

@@ -23,6 +23,7 @@ class _Captured:
 
     def __init__(self):
         self.static = self.ws = self.graph = self.graph2 = self.stage_graphs = self.keep = self.loss = self.hyper = None
+        self.stage_groups = None
 
 
 class GraphedTrainStep:
@@ -35,9 +36,13 @@ class GraphedTrainStep:
     (clip + Adam) waits for the collectives.  If capture is refused the step runs eagerly and a warning says why
     (`strict=True` raises instead).  Up to `max_shapes` input shapes stay captured (least recently used evicted)."""
 
-    def __init__(self, model, optimizer, warmup=3, max_shapes=2, strict=False):
+    def __init__(self, model, optimizer, warmup=3, max_shapes=2, strict=False, dp_graphs=None):
         self.model, self.optimizer, self.warmup = model, optimizer, warmup
         self.max_shapes, self.strict = max_shapes, strict
+        # data parallel only: into how many graphs the R + 2 backward stages are grouped (each graph boundary is a point
+        # where the gradients finished so far start their all-reduce; more graphs = more overlap but more graph launches
+        # and NCCL kernels competing with 1-CTA-per-SM GEMMs).  None: CTN_DP_GRAPHS or 2; R + 2 = one graph per stage.
+        self.dp_graphs = dp_graphs
         self._cap = collections.OrderedDict()  # shape key -> _Captured (graph is None: capture refused, run eagerly)
         self.captured = False
 
@@ -143,6 +148,13 @@ class GraphedTrainStep:
         else:
             one = torch.ones(1, dtype=torch.float32, device=mix.device)
         torch.cuda.synchronize(mix.device)
+        import os
+        nstage = m.R + 2
+        ng = self.dp_graphs if self.dp_graphs is not None else int(os.environ.get("CTN_DP_GRAPHS", "2"))
+        ng = max(1, min(nstage, ng))
+        # stage groups of (nearly) equal size, the first group takes the remainder: [0..a), [a..b), ...
+        bounds = [round(i * nstage / ng) for i in range(ng + 1)]
+        groups = [(bounds[i], bounds[i + 1]) for i in range(ng) if bounds[i + 1] > bounds[i]]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, pool=pool):
             est, ws, token = m._run_forward(mix, training=True)
@@ -151,13 +163,16 @@ class GraphedTrainStep:
             B, C, T = src.shape
             _lib.check(L.ctn_pit_backward(_lib.ptr(src), _lib.ptr(est), _lib.ptr(lens), _lib.ptr(coef), _lib.ptr(one),
                                           B, C, T, _lib.ptr(d_est), _lib.stream()))
-            m._backward_stage(mix, d_est, ws, 0)
+            for stage in range(*groups[0]):
+                m._backward_stage(mix, d_est, ws, stage)
         graphs.append(g)
-        for stage in range(1, m.R + 2):
+        for lo, hi in groups[1:]:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
-                m._backward_stage(mix, d_est, ws, stage)
+                for stage in range(lo, hi):
+                    m._backward_stage(mix, d_est, ws, stage)
             graphs.append(g)
+        c.stage_groups = groups
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, pool=pool):
             self.optimizer.step()
@@ -191,9 +206,9 @@ class GraphedTrainStep:
             c.graph.replay()
         else:
             dp = self._dp()
-            for stage, g in enumerate(c.stage_graphs):
+            for (lo, hi), g in zip(c.stage_groups, c.stage_graphs):
                 g.replay()
-                dp._on_stage(dp.module, stage)  # async all-reduce of the slice this stage finished
+                dp._on_stages(dp.module, lo, hi)  # async all-reduce of the (contiguous) slice these stages finished
             dp._on_stage(dp.module, -1)         # the current stream waits for the collectives
             c.graph2.replay()
         return c.loss

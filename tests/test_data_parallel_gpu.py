@@ -78,7 +78,7 @@ def _worker(rank, world, port, q, backend="nccl"):
     p_eager = model.flat_params.clone()
     model.load_state_dict(sd0)
     opt2 = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
-    step = GraphedTrainStep(dp, opt2, warmup=0)
+    step = GraphedTrainStep(dp, opt2, warmup=0, dp_graphs=cfgd["R"] + 2)  # one graph per backward stage
     losses_g = [step(m.contiguous(), s.contiguous(), l.contiguous()).item() for _ in range(3)]
     cap = next(iter(step._cap.values()))
     assert step.captured and cap.stage_graphs is not None and len(cap.stage_graphs) == cfgd["R"] + 2
@@ -108,8 +108,9 @@ def _worker(rank, world, port, q, backend="nccl"):
     assert err5 < 1e-4, err5
     opt3 = FusedAdam(model, lr=1e-3, max_grad_norm=5.0)
     opt_s = FusedAdam(single, lr=1e-3, max_grad_norm=5.0)
-    step5 = GraphedTrainStep(dp, opt3)
+    step5 = GraphedTrainStep(dp, opt3)  # default grouping: the backward stages in two graphs
     step5(m5, s5, l5)
+    assert len(next(iter(step5._cap.values())).stage_graphs) == 2
     est = single(mix5)
     loss_full, *_ = cal_loss(src5, est, lens5)
     opt_s.zero_grad()

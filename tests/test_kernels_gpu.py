@@ -29,7 +29,8 @@ def cfg_of(**kw):
 
 
 @pytest.mark.parametrize("M,T,N,L", [(2, 403, 16, 8), (3, 32000, 256, 20), (1, 131, 8, 4), (2, 100, 12, 5),
-                                     (2, 2000, 512, 32), (1, 1000, 320, 20)])
+                                     (2, 2000, 512, 32), (1, 1000, 320, 20), (2, 4000, 256, 40), (1, 900, 64, 64),
+                                     (2, 700, 32, 34)])
 def test_encoder_fwd_bwd(M, T, N, L):
     mix, U = rnd(M, T, seed=1, scale=0.1), rnd(N, L, seed=2, scale=0.3)
     K = O.n_frames(T, L)
@@ -223,7 +224,8 @@ def test_batchnorm_stats_and_backward(training, M, K, Ch):
 @pytest.mark.parametrize("softmax", [0, 1])
 @pytest.mark.parametrize("M,K,C,N,L,pad", [(2, 99, 2, 16, 8, 3), (3, 3199, 2, 256, 20, 0), (2, 64, 3, 12, 6, 5),
                                             (1, 40, 2, 8, 5, 0), (2, 33, 4, 8, 4, 1), (2, 150, 4, 512, 32, 2),
-                                            (1, 77, 3, 320, 20, 0), (2, 500, 2, 256, 32, 7)])
+                                            (1, 77, 3, 320, 20, 0), (2, 500, 2, 256, 32, 7), (2, 199, 2, 256, 40, 3),
+                                            (1, 60, 3, 512, 64, 0), (2, 45, 2, 32, 34, 5)])
 def test_decoder_fwd_bwd(softmax, M, K, C, N, L, pad):
     cfg = cfg_of(C=C, N=N, L=L, mask_nonlinear="softmax" if softmax else "relu")
     S = L // 2

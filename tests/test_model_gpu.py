@@ -226,6 +226,8 @@ def test_gradients_against_the_reference_fp32_gradients_table():
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="cLN", causal=True, mask_nonlinear="relu"), 2, 12000),
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="softmax"), 2, 12000),
     (dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="BN", causal=False, mask_nonlinear="relu"), 2, 12000),
+    # the paper's longest filters (L = 40: Luo & Mesgarani Table 2) on a shortened stack
+    (dict(N=256, L=40, B=128, H=256, P=3, X=4, R=2, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu"), 2, 16000),
 ])
 def test_paper_width_against_fp64_oracle(cfgd, M, T):
     """Full-width variants (C=3 six-permutation PIT, causal cLN, softmax mask) against the CPU oracle run in fp64 on
