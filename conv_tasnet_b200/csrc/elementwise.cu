@@ -32,35 +32,112 @@ __device__ __forceinline__ float dprelu(float z, float a) { return z > 0.f ? 1.f
 // ---------------------------------------------------------------------------------------
 // cLN statistics: one warp per frame, two-pass like torch.var (src/conv_tasnet.py:332-333)
 // ---------------------------------------------------------------------------------------
+// 16 bytes of a row: 4 fp32 or 8 bf16 channels -> floats
+template <typename T> struct RowVec;
+template <> struct RowVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    v[4] = v[5] = v[6] = v[7] = 0.f;
+  }
+};
+template <> struct RowVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 w = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(u[i] << 16);
+      v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+};
+
+// One warp per RPW frames.  Rows of up to 512 channels are read ONCE — all of a lane's 16-byte loads of all RPW rows
+// issued back to back (the first version's `for` loop of load + add serialised them: four memory latencies per pass, two
+// passes, one row per warp: 2.6-4.3 TB/s) — and kept in registers for the second pass (the squared deviations, like
+// torch.var); wider rows take the re-reading path.
 template <typename T>
 __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha,
                                                         int64_t F, int Ch, float* __restrict__ rowstat) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int VN = RowVec<T>::N;           // channels per 16-byte load
+  constexpr int NVT = 512 / (32 * VN);       // loads per lane and row (fp32: 4, bf16: 2)
+  constexpr int RPW = VN == 8 ? 1 : 2;       // rows per warp (measured in the config-2 forward, F = 102k x 512: fp32 1 -> 43.5,
+                                             // 2 -> 42.8 us; bf16 1 -> 44.7, 4 -> 59 us (89 registers, 2 blocks per SM))
   const int lane = threadIdx.x & 31;
-  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (f >= F) return;
+  const int64_t f0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (f0 >= F) return;
   const bool hasp = alpha != nullptr;
   const float a = hasp ? __ldg(alpha) : 1.f;
-  const T* row = x + f * Ch;
-  float s = 0.f;
-  for (int c = lane * 4; c < Ch; c += 128) {
-    float4 v = ld4(row + c);
-    if (hasp) v = prelu4(v, a);
-    s += (v.x + v.y) + (v.z + v.w);
+  if (Ch % VN == 0 && Ch <= 512) {
+    float v[RPW][NVT][8];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        const int c = (lane + 32 * i) * VN;
+        if (f0 + r < F && c < Ch) RowVec<T>::load(x + (f0 + r) * Ch + c, v[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (f0 + r >= F) break;  // warp-uniform
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        if ((lane + 32 * i) * VN < Ch) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) {
+            if (hasp) v[r][i][j] = prelu(v[r][i][j], a);
+            s += v[r][i][j];
+          }
+        }
+      }
+      const float mu = warp_sum(s) / (float)Ch;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        if ((lane + 32 * i) * VN < Ch) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) {
+            const float d = v[r][i][j] - mu;
+            q = fmaf(d, d, q);
+          }
+        }
+      }
+      const float var = warp_sum(q) / (float)Ch;
+      if (lane == 0) {
+        rowstat[2 * (f0 + r)] = mu;
+        rowstat[2 * (f0 + r) + 1] = 1.f / sqrtf(var + CTN_EPS);
+      }
+    }
+    return;
   }
-  const float mu = warp_sum(s) / (float)Ch;
-  float q = 0.f;
-  for (int c = lane * 4; c < Ch; c += 128) {
-    float4 v = ld4(row + c);
-    if (hasp) v = prelu4(v, a);
-    const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
-    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-  }
-  const float var = warp_sum(q) / (float)Ch;
-  if (lane == 0) {
-    rowstat[2 * f] = mu;
-    rowstat[2 * f + 1] = 1.f / sqrtf(var + CTN_EPS);
+  for (int r = 0; r < RPW && f0 + r < F; ++r) {
+    const T* row = x + (f0 + r) * Ch;
+    float s = 0.f;
+    for (int c = lane * 4; c < Ch; c += 128) {
+      float4 v = ld4(row + c);
+      if (hasp) v = prelu4(v, a);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mu = warp_sum(s) / (float)Ch;
+    float q = 0.f;
+    for (int c = lane * 4; c < Ch; c += 128) {
+      float4 v = ld4(row + c);
+      if (hasp) v = prelu4(v, a);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float var = warp_sum(q) / (float)Ch;
+    if (lane == 0) {
+      rowstat[2 * (f0 + r)] = mu;
+      rowstat[2 * (f0 + r) + 1] = 1.f / sqrtf(var + CTN_EPS);
+    }
   }
 }
 
@@ -133,7 +210,7 @@ __host__ __device__ inline int dw_blocks(int K, int dil, int tj = DW_TJ) {
   return ncls * ((per_class + tj - 1) / tj);
 }
 
-template <int PT, typename T = float>
+template <int PT, typename T = float, int U_ = CTN_DWF_U>
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ z1, const float* __restrict__ alpha1,
                                                          NormStats st1, const float* __restrict__ gamma1,
                                                          const float* __restrict__ beta1, const float* __restrict__ Wd,
@@ -192,13 +269,13 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T* __restrict__ z
       else w[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float s = 0.f, s2 = 0.f;
-    for (int jj = 0; jj < nj; jj += DWF_U) {
-      // the DWF_U rows that enter the window after each of the next DWF_U outputs: independent loads, issued together
-      float4 nraw[DWF_U]; float2 nst[DWF_U]; bool nok[DWF_U];
+    for (int jj = 0; jj < nj; jj += U_) {
+      // the U_ rows that enter the window after each of the next U_ outputs: independent loads, issued together
+      float4 nraw[U_]; float2 nst[U_]; bool nok[U_];
 #pragma unroll
-      for (int u = 0; u < DWF_U; ++u) fetch(j0 + jj + u + PP - cshift, nraw[u], nst[u], nok[u]);
+      for (int u = 0; u < U_; ++u) fetch(j0 + jj + u + PP - cshift, nraw[u], nst[u], nok[u]);
 #pragma unroll
-      for (int u = 0; u < DWF_U; ++u) {
+      for (int u = 0; u < U_; ++u) {
         if (jj + u < nj) {
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -775,9 +852,9 @@ static int block_for_channels(int Ch) {
 int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s, int bf16) {
   CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
   if (bf16)
-    launch_kernel(row_stats_kernel<__nv_bfloat16>, cdiv(F, 8), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), alpha, F, Ch, rowstat);
+    launch_kernel(row_stats_kernel<__nv_bfloat16>, cdiv(F, 8 * 1), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), alpha, F, Ch, rowstat);
   else
-    launch_kernel(row_stats_kernel<float>, cdiv(F, 8), 256, 0, s, x, alpha, F, Ch, rowstat);
+    launch_kernel(row_stats_kernel<float>, cdiv(F, 8 * 2), 256, 0, s, x, alpha, F, Ch, rowstat);
   return check_launch("row_stats_kernel");
 }
 
@@ -799,9 +876,9 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
     const __nv_bfloat16* zi = reinterpret_cast<const __nv_bfloat16*>(z1);
     __nv_bfloat16* zo = reinterpret_cast<__nv_bfloat16*>(z2);
     if (P == 3)
-      launch_kernel(dwconv_fwd_kernel<3, __nv_bfloat16>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
+      launch_kernel(dwconv_fwd_kernel<3, __nv_bfloat16, 8>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
     else
-      launch_kernel(dwconv_fwd_kernel<0, __nv_bfloat16>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
+      launch_kernel(dwconv_fwd_kernel<0, __nv_bfloat16, 8>, grid, block_for_channels(H), 0, s, zi, alpha1, st1, gamma1, beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);
     return check_launch("dwconv_fwd_kernel<bf16>");
   }
   if (P == 3)

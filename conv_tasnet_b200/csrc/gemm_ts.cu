@@ -710,7 +710,8 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     // 3-deep raw ring and bf16-stored activations (256-cycle k-blocks: wrong tiles, then hangs / launch failures at
     // F = 102k, scratch/run21.sh); latent for a 3-deep A ring.  With even depths a stage belongs to one group, which sees
     // every phase.  (The weight ring and the accumulators are waited on by single threads / all epilogue warps.)
-    a.raw_stages = 2;
+    static const int rst4 = env_int("CTN_TS_RST4", 0);  // experiment: 4-deep raw ring for the one-box flavours
+    a.raw_stages = (rst4 && raw_stage == TS_RAW_BOX) ? 4 : 2;
     a.a_stages &= ~1;
     CTN_REQUIRE(a.a_stages >= 2, "ts_gemm: no room for two operand stages in tensor memory (nmax %d)", a.nmax);
     a.w_stages = (int)((budget - fixed - a.raw_stages * raw_stage) / w_stage);
@@ -719,7 +720,7 @@ int launch_gemm_ts(const GemmArgs& g, cudaStream_t s) {
     {  // debug overrides of the ring depths
       static const int wst = env_int("CTN_TS_WST", 0), rst = env_int("CTN_TS_RST", 0), ast = env_int("CTN_TS_AST", 0);
       if (wst >= 2 && wst <= a.w_stages) a.w_stages = wst;
-      if (rst >= 2 && rst <= a.raw_stages) a.raw_stages = rst & ~1;
+      if (rst >= 2 && rst <= 4) a.raw_stages = rst & ~1;
       if (ast >= 2 && ast <= a.a_stages) a.a_stages = ast & ~1;
     }
     smem = a.w_stages * w_stage + a.raw_stages * raw_stage + fixed;
