@@ -671,9 +671,11 @@ static int model_backward(const Ctx& X, const float* mixture, const float* d_est
       CTN_TRY(launch_wgrad(wa, s));
     }
     // gLN: the backward of norm2 (+ PReLU) is elementwise given the per-sample sums, so the depthwise backward can apply
-    // it while it loads dn2 / z2 (no gln_bwd_apply pass over [F, H]).  Built, parity-tested and measured: the fused kernel
-    // saves a launch and 2 H elements per frame of traffic but lowers the step from 5.95 to 6.08 ms (elementwise.cu), so it
-    // is opt-in (CTN_APPLY_FUSION=1).  cLN needs per-frame means and BatchNorm per-channel coefficients: separate pass.
+    // it as the dn2 / z2 rows enter its window (no gln_bwd_apply pass over [F, H]).  Built, parity-tested and measured in
+    // three forms (register window, two-phase shared-memory tile, every tile staged by bulk copies): the last one is the
+    // fastest (30.3 us in place against 19.8 + 12.6 us for the two kernels) but at 104 KB of tiles only two blocks fit an
+    // SM and the graph-replayed step is 5.91 against 5.80 ms, so it stays opt-in (CTN_APPLY_FUSION=1).  cLN needs
+    // per-frame means and BatchNorm per-channel coefficients: separate pass.
     static const bool apply_fusion = env_flag("CTN_APPLY_FUSION");
     if (gln && apply_fusion) {
       CTN_TRY(run_dwconv_bwd_gln_fused(dn2, X.z2(b), X.blk(b, L.a2), st2, X.blk(b, L.g2), X.red(b, 1), gblk(b, L.a2),
