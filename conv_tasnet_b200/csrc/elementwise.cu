@@ -231,7 +231,6 @@ constexpr int DWF_TJ = CTN_DWF_TJ;  // forward (no partial rows: its tile can di
                                     // (M = 3 x 4 s): eager in-place timing favours (32, 8) (16.4 vs 18.1 us) but the
                                     // graph-replayed step is fastest with (16, 4): 6.29 vs 6.36 ms (register footprint
                                     // under programmatic dependent launch); (8, 8) 25 us, (64, 8) 21 us
-constexpr int DWF_U = CTN_DWF_U;
 constexpr int MAXP = 8;
 
 __host__ __device__ inline int dw_classes(int K, int dil) { return dil < K ? dil : K; }
