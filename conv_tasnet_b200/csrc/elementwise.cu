@@ -232,6 +232,8 @@ constexpr int DWF_TJ = CTN_DWF_TJ;  // forward (no partial rows: its tile can di
                                     // graph-replayed step is fastest with (16, 4): 6.29 vs 6.36 ms (register footprint
                                     // under programmatic dependent launch); (8, 8) 25 us, (64, 8) 21 us
 constexpr int MAXP = 8;
+// the bulk-staged kernels issue one row copy per lane of warp 0 and keep per-row metadata in TJ + MAXP slots
+static_assert(DW_TJ + MAXP - 1 <= 32 && DWF_TJ + MAXP - 1 <= 32, "depthwise tiles: at most 32 staged rows per tensor");
 
 __host__ __device__ inline int dw_classes(int K, int dil) { return dil < K ? dil : K; }
 __host__ __device__ inline int dw_blocks(int K, int dil, int tj = DW_TJ) {
