@@ -6,7 +6,7 @@ SO=conv_tasnet_b200/libctn_b200.so
 cuobjdump -sass $SO > /tmp/ctn.sass 2>/dev/null
 {
   echo "# cuobjdump -sass $SO | grep -c <mnemonic>   ($(date -u +%Y-%m-%d), sources $(git rev-parse --short HEAD)+)"
-  for m in UTCHMMA UTCQMMA "UTCHMMA.*TS\|UTCHMMA.2CTA" UTMALDG UTMALDG.2D.MULTICAST UTMAREDG UTMASTG LDTM STTM UTCBAR UTCBAR.MULTICAST UTCATOMSWS "SYNCS" "ELECT" LDGSTS "ACQBULK\|UCGABAR"; do
+  for m in UTCHMMA UTCQMMA "UTCHMMA.*TS\|UTCHMMA.2CTA" UTMALDG UTMALDG.2D.MULTICAST UTMAREDG UTMASTG LDTM STTM UTCBAR UTCBAR.MULTICAST UTCATOMSWS "SYNCS" "ELECT" LDGSTS "ACQBULK\|UCGABAR" UBLKCP; do
     printf "%-28s %s\n" "$m" "$(grep -c "$m" /tmp/ctn.sass)"
   done
   echo "# per kernel (function name : UTCHMMA / UTMALDG / LDTM / STTM / UTMAREDG)"
