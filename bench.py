@@ -40,7 +40,7 @@ import torch  # noqa: E402
 PAPER = dict(N=256, L=20, B=256, H=512, P=3, X=8, R=4, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu")
 SR = 8000
 PAPER_STR = "N=256 L=20 B=256 H=512 P=3 X=8 R=4"
-TRAIN_STR = "training step = fwd + PIT SI-SNR + bwd (+ NCCL grad all-reduce) + clip(5) + Adam"
+TRAIN_STR = "training step = fwd + PIT SI-SNR + bwd (+ gradient all-reduce over NVLink) + clip(5) + Adam"
 CONFIGS = {
     0: dict(model={}, M=1, seconds=4, mode="fwd_loss",
             workload=f"configs[0]: paper config {PAPER_STR} C=2 gLN non-causal, one 4 s @ 8 kHz mixture, fp32 forward + cal_loss"),
@@ -258,6 +258,10 @@ def main():
     ap.add_argument("--dtype", default=None, choices=["f32", "bf16"], help="forward modes only: bf16 = the reduced-precision "
                     "inference path (default: the config's own, bf16 for --config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
+                    help="N > 1 training: gradient exchange = the one-kernel peer-memory all-reduce inside the step's graph "
+                         "(csrc/peer_reduce.cu) or bucketed NCCL all-reduces between per-stage graphs; default: "
+                         "CTN_EXCHANGE or peer")
     ap.add_argument("--profile-only", action="store_true", help="run only warm-up + K device-resident steps (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                     "one captured CUDA graph per step")
@@ -303,7 +307,17 @@ def main():
     if dtype == "bf16":
         model.half_inference(True)
     # data parallel training shards the batch and all-reduces gradients; inference shards by utterance with no collective
-    dp = ShardedDataParallel(model) if (world > 1 and train) else model
+    exchange = args.exchange or os.environ.get("CTN_EXCHANGE", "peer")
+    if world > 1 and train:
+        try:
+            dp = ShardedDataParallel(model, peer_reduce=(exchange == "peer"))
+        except RuntimeError as e:  # (collective: the set-up fails on every rank or on none) fall back to NCCL
+            if rank == 0:
+                sys.stderr.write(f"bench: peer-memory exchange unavailable ({e}); using NCCL\n")
+            exchange = "nccl"
+            dp = ShardedDataParallel(model, peer_reduce=False)
+    else:
+        dp = model
     opt = FusedAdam(model, lr=1e-3, max_grad_norm=5.0) if train else None
     mix_h, src_h, len_h = synthetic(M, T, kw["C"], kw["L"], 1234 + args.config + rank)
     mix_h, src_h, len_h = mix_h.pin_memory(), src_h.pin_memory(), len_h.pin_memory()
@@ -523,6 +537,12 @@ def main():
                                  "frac_of_hbm_bound": (step_bytes / world / (pk["hbm_gbs"] * 1e9)) / t_step}}
     if fwd_line is not None:
         line["fwd"] = fwd_line
+    if world > 1 and train:
+        peer = getattr(dp, "peer_active", lambda: False)()
+        line["exchange"] = ("one-kernel peer-memory all-reduce over NVLink inside the step's CUDA graph (csrc/peer_reduce.cu)"
+                            if peer else "bucketed NCCL all-reduce between per-stage CUDA graphs")
+        if peer and dp._peer.error():
+            line["exchange_error"] = "a rank did not arrive within the kernel's timeout"
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt, sample, cores = reference_steps(args.config, mode, 2, 1, budget_s=30.0)

@@ -44,6 +44,12 @@ SIGNATURES = {
     "ctn_sisnri": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ctn_reorder_source": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "ctn_overlap_and_add": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ctn_peer_alloc": (c_i32, [c_i64, ctypes.POINTER(c_vp)]),
+    "ctn_peer_free": (c_i32, [c_vp]),
+    "ctn_peer_export": (c_i32, [c_vp, ctypes.c_char_p]),
+    "ctn_peer_open": (c_i32, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "ctn_peer_close": (c_i32, [c_vp]),
+    "ctn_peer_all_reduce": (c_i32, [ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_i32, c_i32, c_i64, c_i64, c_f32, c_vp]),
     "ctn_clip_grad_norm": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "ctn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp]),
     "ctn_encoder_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

@@ -11,27 +11,151 @@ items, so the global-batch-mean gradient is sum_r (M_r / M_global) g_r.  The wra
 (4 bytes, asynchronous, no host sync) in every training forward and scales the incoming d_est of the model's backward
 by world * M_r / M_global on the device; the AVG all-reduce of the gradients then yields exactly that weighted sum.
 
+Peer-memory exchange (`peer_reduce=True`, or CTN_PEER_REDUCE=1): the flat gradient buffer of every rank is a CUDA-IPC
+allocation mapped by all ranks of the node, and the whole all-reduce is ONE hand-written kernel per step
+(csrc/peer_reduce.cu: flag barrier, reduce-scatter with peer loads in rank order, all-gather with peer stores, flag
+barrier) launched on the compute stream after the last backward stage — no NCCL call and nothing for the host to do, so
+`graph.GraphedTrainStep` captures the data-parallel step as a single CUDA graph exactly like the single-GPU step.
+
 The wrapper exposes `.module`, `__call__`, `.parameters()`, `.train()/.eval()`, `.cuda()` so the reference's
 solver.py (which expects a DataParallel-style object, solver.py:61,97,141,188,194) runs unchanged.
 """
+import ctypes
+import os
+import socket
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import _lib
+
+
+class _RawCuda:
+    """a device allocation that torch did not make, exposed through __cuda_array_interface__ (zero-copy torch.as_tensor)"""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerExchange:
+    """This rank's exchange buffer (256-byte flag block + `n_floats` fp32) in CUDA-IPC memory, every other rank's buffer
+    mapped into this process, and the one-kernel all-reduce over them (include/ctn_b200.h: ctn_peer_*).
+
+    All ranks of the group must sit on one node (NVLink / NVSwitch peers) and construct it collectively."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, n_floats, device, group=None):
+        L = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if not 2 <= self.world <= 8:
+            raise RuntimeError(f"PeerExchange: world size {self.world} not in [2, 8]")
+        self.n = int(n_floats)
+        self.device = torch.device(device)
+        self._base, self._peers = None, []
+        nbytes = self.FLAG_BYTES + 4 * self.n
+        err = None
+        try:
+            with torch.cuda.device(self.device):
+                p = ctypes.c_void_p()
+                _lib.check(L.ctn_peer_alloc(nbytes, ctypes.byref(p)))
+                self._base = p.value
+                h = ctypes.create_string_buffer(64)
+                _lib.check(L.ctn_peer_export(self._base, h))
+                mine = (bytes(h.raw), socket.gethostname(), os.getpid())
+        except Exception as e:  # every rank still takes part in the exchange below, then all of them give up together
+            err, mine = e, (None, socket.gethostname(), os.getpid())
+        table = [None] * self.world
+        dist.all_gather_object(table, mine, group=group)
+        if err is None and (any(t[0] is None for t in table) or len({t[1] for t in table}) != 1):
+            err = RuntimeError("PeerExchange: a rank could not allocate / export its buffer, or the ranks are on "
+                               "different hosts")
+        bases = [None] * self.world
+        if err is None:
+            try:
+                with torch.cuda.device(self.device):
+                    for r, (handle, _host, _pid) in enumerate(table):
+                        if r == self.rank:
+                            bases[r] = self._base
+                        else:
+                            q = ctypes.c_void_p()
+                            _lib.check(L.ctn_peer_open(handle, ctypes.byref(q)))
+                            bases[r] = q.value
+                            self._peers.append(q.value)
+            except Exception as e:
+                err = e
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            self.close()
+            raise RuntimeError(f"PeerExchange: set-up failed on some rank ({err})")
+        self._bufs = (ctypes.c_void_p * self.world)(*[b + self.FLAG_BYTES for b in bases])
+        self._flags = (ctypes.c_void_p * self.world)(*bases)
+        self.tensor = torch.as_tensor(_RawCuda(self._base + self.FLAG_BYTES, self.n), device=self.device)
+        self._flag_view = torch.as_tensor(_RawCuda(self._base, self.FLAG_BYTES // 4), device=self.device).view(torch.int32)
+
+    def all_reduce(self, scale=None, offset=0, count=None):
+        """sum over the ranks (x scale, default 1 / world) of floats [offset, offset + count) of the exchange buffers,
+        left in every rank's buffer; one kernel on the current stream"""
+        count = self.n - offset if count is None else count
+        scale = 1.0 / self.world if scale is None else scale
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ctn_peer_all_reduce(self._bufs, self._flags, self.rank, self.world, offset, count,
+                                                      scale, _lib.stream()))
+
+    def error(self):
+        """True when a wait inside the kernel gave up (a rank never arrived); synchronises"""
+        return bool(self._flag_view[18].item())
+
+    def close(self):
+        L = _lib.lib()
+        for q in self._peers:
+            L.ctn_peer_close(q)
+        self._peers = []
+        if self._base is not None:
+            L.ctn_peer_free(self._base)
+            self._base = None
+
+
 
 class ShardedDataParallel(nn.Module):
-    def __init__(self, module, process_group=None, overlap=True, broadcast_parameters=True, weight_by_batch=True):
+    def __init__(self, module, process_group=None, overlap=True, broadcast_parameters=True, weight_by_batch=True,
+                 peer_reduce=None):
         super().__init__()
         self.module = module
         self.process_group = process_group
         self.overlap = overlap
         self.weight_by_batch = weight_by_batch
         self._pending = []
+        self._peer = None
         self._enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         if self._enabled:
             module._grad_sync = self._on_stage
             if broadcast_parameters:
                 self.broadcast_parameters()
+            if peer_reduce is None:
+                peer_reduce = os.environ.get("CTN_PEER_REDUCE", "0") == "1"
+            if peer_reduce:
+                self.enable_peer_reduce()
+
+    def enable_peer_reduce(self):
+        """Move the flat gradient buffer into CUDA-IPC memory shared with the other ranks of the node and exchange
+        gradients with the one-kernel peer all-reduce instead of NCCL (collective: every rank calls it)."""
+        m = self.module
+        flat = m.flat_params
+        self._peer = PeerExchange(flat.numel(), flat.device, self.process_group)
+        for p in m.parameters():
+            p.grad = None
+        m._flat_grad = self._peer.tensor
+
+    def peer_active(self):
+        """the model's flat gradient buffer still is the shared one (a re-flatten, e.g. after .to(), drops it)"""
+        return self._peer is not None and self.module.flat_grads.data_ptr() == self._peer.tensor.data_ptr()
+
+    def peer_all_reduce(self):
+        self._peer.all_reduce()
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s weights (once; DataParallel re-broadcasts every step)."""
@@ -60,6 +184,10 @@ class ShardedDataParallel(nn.Module):
     # called by ConvTasNet._run_backward after each backward stage (stage >= 0), once to drain (stage == -1), and with
     # stage == -2 + an explicit buffer from the slow path (gradients computed aside): synchronous whole-buffer reduce
     def _on_stage(self, model, stage, buf=None):
+        if stage != -2 and self.peer_active():  # one kernel for the whole buffer, after the last stage
+            if stage == -1:
+                self._peer.all_reduce()
+            return
         if stage == -2:
             self._reduce(buf)
             self._drain()
@@ -99,6 +227,9 @@ class ShardedDataParallel(nn.Module):
     def all_reduce_flat(self):
         """Un-overlapped variant: all-reduce the whole flat gradient buffer in R+2 bucket calls."""
         if not self._enabled:
+            return
+        if self.peer_active():
+            self._peer.all_reduce()
             return
         for stage in range(self.module.R + 2):
             self._on_stage(self.module, stage)

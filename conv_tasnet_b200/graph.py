@@ -117,6 +117,8 @@ class GraphedTrainStep:
                     with torch.cuda.graph(g):
                         c.loss = self._eager(*c.static)
                     c.graph = g
+                elif dp.peer_active():  # the exchange is a kernel of ours: the whole step is one graph
+                    self._capture_peer(dp, c)
                 else:  # collectives stay eager, between the per-stage graphs
                     self._capture_staged(dp, c)
             except Exception as e:  # capture refused: keep working, eagerly — but say so
@@ -128,6 +130,38 @@ class GraphedTrainStep:
         finally:
             m._ws_override = None
         return c
+
+    def _capture_peer(self, dp, c):
+        """data parallel with the peer-memory exchange: forward + PIT + every backward stage + the one-kernel all-reduce
+        (csrc/peer_reduce.cu) + clip + Adam in ONE graph — nothing stays on the host between the kernels"""
+        m = dp.module
+        mix, src, lens = c.static
+        lens = lens.to(torch.int64)
+        L = _lib.lib()
+        if any(p.grad is None for p in m.parameters()):
+            for p, v in zip(m.parameters(), m.grad_views()):
+                p.grad = v
+        # uneven shards: the weight world * M_local / M_global of this rank's loss gradient (see _capture_staged)
+        if getattr(dp, "weight_by_batch", False):
+            one = dp.grad_scale_for(mix.shape[0], mix.device).to(torch.float32).clone()
+        else:
+            one = torch.ones(1, dtype=torch.float32, device=mix.device)
+        torch.cuda.synchronize(mix.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            est, ws, token = m._run_forward(mix, training=True)
+            loss, _max_snr, _idx, coef, _ = _pit_forward_raw(src, est, lens, False)
+            d_est = torch.empty_like(est)
+            B, C, T = src.shape
+            _lib.check(L.ctn_pit_backward(_lib.ptr(src), _lib.ptr(est), _lib.ptr(lens), _lib.ptr(coef), _lib.ptr(one),
+                                          B, C, T, _lib.ptr(d_est), _lib.stream()))
+            for stage in range(m.R + 2):
+                m._backward_stage(mix, d_est, ws, stage)
+            dp.peer_all_reduce()
+            self.optimizer.step()
+        c.keep = (est, ws, token, coef, d_est, one, lens)  # tensors the graph references
+        c.loss = loss.view(())
+        c.graph, c.graph2, c.stage_graphs, c.stage_groups = g, None, None, None
 
     def _capture_staged(self, dp, c):
         """forward + loss + backward as R+2 graphs cut at the gradient-bucket boundaries (driving the C ABI directly:

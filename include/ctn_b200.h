@@ -144,6 +144,27 @@ int32_t ctn_assemble_batch(const float* packed_mix, const float* packed_src, con
 int32_t ctn_pack_valid(const float* inputs, const int64_t* lengths, const int64_t* out_offsets, int32_t B,
                        int32_t C, int32_t T, float* packed, cudaStream_t stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (replaces nn.DataParallel's gather of the replicas'
+ * gradients, src/train.py:83-85 / src/solver.py:194) ------------------------------------------------------------
+ * Every rank of the node allocates its exchange buffer with ctn_peer_alloc (a CUDA allocation of its own, zero-filled),
+ * exports it (64-byte CUDA-IPC handle, carried to the other processes by the caller, e.g. torch.distributed
+ * all_gather_object), and maps every other rank's buffer with ctn_peer_open.  Layout of a buffer, by convention of the
+ * caller: a 256-byte flag block (uint32, zero at start: barrier slots, epoch, block counter, error word [18]) followed
+ * by the flat fp32 gradient buffer. */
+int32_t ctn_peer_alloc(int64_t bytes, void** ptr);
+int32_t ctn_peer_free(void* ptr);
+int32_t ctn_peer_export(const void* ptr, uint8_t* handle64);
+int32_t ctn_peer_open(const uint8_t* handle64, void** ptr);
+int32_t ctn_peer_close(void* ptr);
+/* ONE kernel: wait until every rank's gradients are complete, sum floats [offset, offset + count) of the `world` buffers
+ * in rank order, multiply by `scale` and leave the result in EVERY rank's buffer (each rank reduces 1/world of the range
+ * with peer loads and writes it to all ranks with peer stores), wait until every rank's share has landed.  bufs_host /
+ * flags_host: HOST arrays of `world` device pointers (entry `rank` is this rank's own memory, the others are the
+ * ctn_peer_open mappings).  Every rank must launch it once per exchange with the same offset / count / world (2..8);
+ * offset and count multiples of 4.  Stream-ordered, no host synchronisation, capturable into a CUDA graph. */
+int32_t ctn_peer_all_reduce(float* const* bufs_host, uint32_t* const* flags_host, int32_t rank, int32_t world,
+                            int64_t offset, int64_t count, float scale, cudaStream_t stream);
+
 /* ---- step tail (solver.py:192-196: clip_grad_norm_ + Adam) on the flat buffers ----------- */
 /* total L2 norm -> norm_out[0]; grads *= min(1, max_norm/(norm+1e-6)) like torch clip_grad_norm_.
  * scratch: >= 8 * 1024 bytes */

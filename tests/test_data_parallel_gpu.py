@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, backend="nccl"):
+def _worker(rank, world, port, q, backend="nccl", peer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if backend == "nccl":
         torch.cuda.set_device(rank)
@@ -39,7 +39,8 @@ def _worker(rank, world, port, q, backend="nccl"):
     cfgd = dict(N=64, L=20, B=128, H=128, P=3, X=3, R=2, C=2, norm_type="gLN", causal=False, mask_nonlinear="relu")
     torch.manual_seed(7 + rank)  # replicas start different; the wrapper broadcasts rank 0's weights
     model = ConvTasNet(**cfgd).cuda().train()
-    dp = ShardedDataParallel(model)
+    dp = ShardedDataParallel(model, peer_reduce=peer)
+    assert dp.peer_active() == peer
     mix, src, lens = O.synthetic_batch(4, 4000, 2, 20, 11)
     mix, src, lens = mix.cuda(), src.cuda(), lens.cuda()
     m, s, l = shard_batch(rank, world, mix, src, lens)
@@ -81,7 +82,10 @@ def _worker(rank, world, port, q, backend="nccl"):
     step = GraphedTrainStep(dp, opt2, warmup=0, dp_graphs=cfgd["R"] + 2)  # one graph per backward stage
     losses_g = [step(m.contiguous(), s.contiguous(), l.contiguous()).item() for _ in range(3)]
     cap = next(iter(step._cap.values()))
-    assert step.captured and cap.stage_graphs is not None and len(cap.stage_graphs) == cfgd["R"] + 2
+    if peer:  # the exchange is a kernel inside the step's single graph
+        assert step.captured and cap.stage_graphs is None and cap.graph2 is None
+    else:
+        assert step.captured and cap.stage_graphs is not None and len(cap.stage_graphs) == cfgd["R"] + 2
     assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-4, (losses_e, losses_g)
     # The two runs are not bit-identical (split-K weight gradients are added in arrival order), and Adam's first steps move
     # every element by ~lr * sign(g): an element whose gradient is at rounding level may go the other way (2 * lr per
@@ -117,7 +121,7 @@ def _worker(rank, world, port, q, backend="nccl"):
     opt_s = FusedAdam(single, lr=1e-3, max_grad_norm=5.0)
     step5 = GraphedTrainStep(dp, opt3)  # default grouping: the backward stages in two graphs
     step5(m5, s5, l5)
-    assert len(next(iter(step5._cap.values())).stage_graphs) == 2
+    assert peer or len(next(iter(step5._cap.values())).stage_graphs) == 2
     est = single(mix5)
     loss_full, *_ = cal_loss(src5, est, lens5)
     opt_s.zero_grad()
@@ -128,8 +132,79 @@ def _worker(rank, world, port, q, backend="nccl"):
     g_graph, g_single = model.flat_grads, single.flat_grads
     assert ((g_graph - g_single).norm() / g_single.norm()).item() < 1e-4
     assert abs(opt3.grad_norm.item() - opt_s.grad_norm.item()) < 1e-4 * opt_s.grad_norm.item()
+    if peer:
+        assert not dp._peer.error()
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _peer_worker(rank, world, port, backend, same_gpu):
+    """the one-kernel peer-memory all-reduce (csrc/peer_reduce.cu) against the same sum formed by torch, bit for bit"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = 0 if same_gpu else rank
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from conv_tasnet_b200.data_parallel import PeerExchange
+    n = 1_000_004  # a multiple of 4 that does not split evenly over the ranks' slices
+    ex = PeerExchange(n, torch.device("cuda", dev))
+    assert ex.tensor.data_ptr() % 16 == 0 and ex.tensor.numel() == n
+    for it in range(4):  # the flags are reused: epochs must keep the rounds apart
+        parts = []
+        for r in range(world):
+            g = torch.Generator(device="cpu").manual_seed(100 * it + r)
+            parts.append(torch.randn(n, generator=g))
+        ex.tensor.copy_(parts[rank])
+        want = parts[0].clone()
+        for r in range(1, world):
+            want += parts[r]  # rank order, like the kernel
+        want *= 1.0 / world
+        ex.all_reduce()
+        torch.cuda.synchronize()
+        assert not ex.error()
+        assert torch.equal(ex.tensor.cpu(), want), (it, (ex.tensor.cpu() - want).abs().max().item())
+    # a sub-range leaves the rest of the buffer alone
+    ex.tensor.fill_(float(rank + 1))
+    ex.all_reduce(scale=1.0, offset=1000, count=4000)
+    torch.cuda.synchronize()
+    out = ex.tensor.cpu()
+    total = float(sum(range(1, world + 1)))
+    assert (out[1000:5000] == total).all() and (out[:1000] == rank + 1).all() and (out[5000:] == rank + 1).all()
+    dist.barrier()
+    ex.close()
+    dist.destroy_process_group()
+
+
+def test_peer_all_reduce_kernel_two_ranks_on_one_gpu():
+    mp.spawn(_peer_worker, args=(2, _free_port(), "gloo", True), nprocs=2, join=True)
+
+
+def test_sharded_dp_with_peer_exchange_two_ranks_on_one_gpu():
+    """the data-parallel step with the peer-memory exchange instead of NCCL: sharded gradients = full-batch gradients,
+    identical on both ranks, and the single-graph step follows the eager one"""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(2, _free_port(), q, "gloo", True), nprocs=2, join=True)
+    err = q.get()
+    assert err < 1e-4, err
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_all_reduce_kernel_two_gpus():
+    mp.spawn(_peer_worker, args=(2, _free_port(), "nccl", False), nprocs=2, join=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_dp_with_peer_exchange_two_gpus():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(2, _free_port(), q, "nccl", True), nprocs=2, join=True)
+    err = q.get()
+    assert err < 1e-4, err
 
 
 def test_sharded_dp_equals_full_batch_two_ranks_on_one_gpu_gloo():
