@@ -11,7 +11,8 @@ items, so the global-batch-mean gradient is sum_r (M_r / M_global) g_r.  The wra
 (4 bytes, asynchronous, no host sync) in every training forward and scales the incoming d_est of the model's backward
 by world * M_r / M_global on the device; the AVG all-reduce of the gradients then yields exactly that weighted sum.
 
-Peer-memory exchange (`peer_reduce=True`, or CTN_PEER_REDUCE=1): the flat gradient buffer of every rank is a CUDA-IPC
+Peer-memory exchange (the default under an NCCL process group of at most 8 ranks on one node; `peer_reduce=False` or
+CTN_PEER_REDUCE=0 keeps the bucketed NCCL all-reduces): the flat gradient buffer of every rank is a CUDA-IPC
 allocation mapped by all ranks of the node, and the whole all-reduce is ONE hand-written kernel per step
 (csrc/peer_reduce.cu: flag barrier, reduce-scatter with peer loads in rank order, all-gather with peer stores, flag
 barrier) launched on the compute stream after the last backward stage — no NCCL call and nothing for the host to do, so
@@ -135,8 +136,19 @@ class ShardedDataParallel(nn.Module):
             module._grad_sync = self._on_stage
             if broadcast_parameters:
                 self.broadcast_parameters()
-            if peer_reduce is None:
-                peer_reduce = os.environ.get("CTN_PEER_REDUCE", "0") == "1"
+            if peer_reduce is None:  # default: on wherever it can work (NCCL group = one GPU per rank, at most 8 of them)
+                env = os.environ.get("CTN_PEER_REDUCE")
+                auto = (dist.get_backend(process_group) == "nccl" and dist.get_world_size(process_group) <= 8
+                        and module.flat_params.is_cuda)
+                if env is not None:
+                    peer_reduce = env == "1"
+                elif auto:  # the set-up fails on every rank or on none (PeerExchange agrees on it): NCCL otherwise
+                    try:
+                        self.enable_peer_reduce()
+                    except RuntimeError as e:
+                        import warnings
+                        warnings.warn(f"ShardedDataParallel: peer-memory gradient exchange unavailable ({e}); using NCCL")
+                    peer_reduce = False
             if peer_reduce:
                 self.enable_peer_reduce()
 

@@ -198,6 +198,12 @@ def test_peer_all_reduce_kernel_two_gpus():
     mp.spawn(_peer_worker, args=(2, _free_port(), "nccl", False), nprocs=2, join=True)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 3, reason="needs more than 2 GPUs")
+def test_peer_all_reduce_kernel_every_gpu_of_the_node():
+    n = min(torch.cuda.device_count(), 8)
+    mp.spawn(_peer_worker, args=(n, _free_port(), "nccl", False), nprocs=n, join=True)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_dp_with_peer_exchange_two_gpus():
     ctx = mp.get_context("spawn")
