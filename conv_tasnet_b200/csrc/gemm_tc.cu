@@ -90,7 +90,6 @@ template <bool TF32, bool FOLD, bool RES, bool STATS, bool NRED = false>
 __global__ void __launch_bounds__(TF32 ? 128 + CONV_THREADS : 128 + CONV_THREADS_BF16, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_a, TcGemmArgs a) {
-  pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   // converter / epilogue threads: the bf16 (gradient) flavour runs 16 warps (measured: its longer K loop gains from the
   // extra converters and its one-accumulator epilogue fits the register budget), the TF32 flavour 8 (150 registers)
   constexpr int CT = TF32 ? CONV_THREADS : CONV_THREADS_BF16;
@@ -158,6 +157,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // dependents may be scheduled only now that this CTA owns its tensor memory: a dependent CTA that became resident
+  // earlier could allocate first and then sit in griddepcontrol.wait on a grid whose CTA is blocked in tcgen05.alloc
+  pdl_launch_dependents();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global data is touched only below
   if (threadIdx.x == 0) TR(1);
   // TMEM accumulators (NF fp32 columns each).  The tensor core truncates (round-toward-zero) when it adds into its
@@ -508,7 +510,6 @@ constexpr int WNG = CTN_WNG;               // converter groups, taking k-blocks 
 constexpr int W_THREADS = 128 + WNG * WGT; // 4 control warps + the converter / epilogue warps
 template <int NI>
 __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dw, TcWgradArgs a) {
-  pdl_launch_dependents();  // the wait follows the prologue (barrier init, TMEM allocation)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   constexpr int A_PLANE = WK * BM * 2;   // 8 KB   (2 groups of 64 o-columns x 32 rows x 128 B)
@@ -544,6 +545,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) tc_wgrad_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // dependents may be scheduled only now that this CTA owns its tensor memory: a dependent CTA that became resident
+  // earlier could allocate first and then sit in griddepcontrol.wait on a grid whose CTA is blocked in tcgen05.alloc
+  pdl_launch_dependents();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global data is touched only below
   if (threadIdx.x == 0) TR(1);
 
