@@ -9,7 +9,8 @@ int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t
 int run_prep_normfold(const float*, const float*, const float*, int, int, int, int64_t, float*, float*, float*, int64_t,
                       int64_t, cudaStream_t);
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
-                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0);
+                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0, float* rs1_out = nullptr,
+                   float* rs2_out = nullptr);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_dwconv_bwd_gln_fused(const float*, const float*, const float*, NormStats, const float*, const double*, float*,

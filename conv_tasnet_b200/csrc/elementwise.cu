@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(256) dwconv_fwd_bulk_kernel(const T* __restric
                                                               const float* __restrict__ Wd, int K, int H, int P, int dil,
                                                               int cshift, T* __restrict__ z2,
                                                               double* __restrict__ stat_out,
-                                                              const float* __restrict__ alpha2) {
+                                                              const float* __restrict__ alpha2,
+                                                              float* __restrict__ rs1_out,
+                                                              float* __restrict__ rs2_out) {
   pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t ew_dsm[];
   T* tile = reinterpret_cast<T*>(ew_dsm);  // [DWF_TJ + PP - 1][H]
@@ -397,19 +399,73 @@ __global__ void __launch_bounds__(256) dwconv_fwd_bulk_kernel(const T* __restric
     // (dil = 1: one copy of the whole contiguous range instead of a copy per row measured the same, 13.7 vs 14.0 us)
     if (ok) ew_bulk_load(tile + (size_t)threadIdx.x * H, z1 + (base + k) * H, (uint32_t)(H * sizeof(T)), &bar);
   }
+  // cLN (rs1_out / rs2_out given): the per-frame statistics are formed HERE from the staged rows — of prelu(z1) for every
+  // input row the block holds (two passes over shared memory, like torch.var) and of prelu(z2) for its output rows, which
+  // are kept in the shared-memory rows their inputs have left — instead of two row_stats passes over [F, H] per block
+  // (21 % of the causal-cLN forward).  Rows the block owns as outputs are also written out for the later consumers.
+  const bool own_stats = rs1_out != nullptr;
   if ((int)threadIdx.x < nrows) {
     const int idx = idx0 + (int)threadIdx.x, k = r + idx * dil;
     const bool ok = idx >= 0 && k < K;
     float mu = 0.f, rr = 0.f;  // rr = 0 marks a padding row
-    if (ok) load_stats(st1, m, base + k, mu, rr);
-    s_rs[threadIdx.x] = make_float2(mu, ok ? rr : 0.f);
+    if (ok && !own_stats) load_stats(st1, m, base + k, mu, rr);
+    s_rs[threadIdx.x] = make_float2(mu, ok ? (own_stats ? 1.f : rr) : 0.f);
   }
   const float a1 = __ldg(alpha1);
   const bool do_stats = stat_out != nullptr;
-  const float a2 = do_stats ? __ldg(alpha2) : 1.f;
+  const float a2 = (do_stats || rs2_out != nullptr) ? __ldg(alpha2) : 1.f;
   __syncthreads();
   double acc[2] = {0.0, 0.0};
   bool waited = false;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // (mean, rstd) over the H channels of prelu(row, slope): one warp per row, the summation order of row_stats_kernel
+  auto row_stats_of = [&](const T* rowp, float slope, float& mu, float& rstd) {
+    float sum = 0.f, q = 0.f;
+    if (H <= 512) {  // the lane's (up to 16) values stay in registers between the two passes
+      float4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int c = lane * 4 + 128 * t;
+        v[t] = c < H ? prelu4(ld4(rowp + c), slope) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += v[t].x; sum += v[t].y; sum += v[t].z; sum += v[t].w;
+      }
+      mu = warp_sum(sum) / (float)H;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (lane * 4 + 128 * t < H) {
+          const float d0 = v[t].x - mu, d1 = v[t].y - mu, d2 = v[t].z - mu, d3 = v[t].w - mu;
+          q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+        }
+      }
+    } else {
+      for (int c = lane * 4; c < H; c += 128) {
+        const float4 v = prelu4(ld4(rowp + c), slope);
+        sum += v.x; sum += v.y; sum += v.z; sum += v.w;
+      }
+      mu = warp_sum(sum) / (float)H;
+      for (int c = lane * 4; c < H; c += 128) {
+        const float4 v = prelu4(ld4(rowp + c), slope);
+        const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+      }
+    }
+    rstd = 1.f / sqrtf(warp_sum(q) / (float)H + CTN_EPS);
+  };
+  if (own_stats) {
+    ew_mbar_wait(&bar, 0);
+    waited = true;
+    for (int i = wid; i < nrows; i += nwarp) {
+      if (s_rs[i].y == 0.f) continue;  // padding row (warp-uniform)
+      float mu, rstd;
+      row_stats_of(tile + (size_t)i * H, a1, mu, rstd);
+      if (lane == 0) {
+        s_rs[i] = make_float2(mu, rstd);
+        if (i >= cshift && i < cshift + nj)  // tile row i = output frame j0 + i - cshift: written once, by its owner
+          reinterpret_cast<float2*>(rs1_out)[base + r + (int64_t)(idx0 + i) * dil] = make_float2(mu, rstd);
+      }
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     const float4 g = ld4(gamma1 + c), b = ld4(beta1 + c);
     float wd[4][NP_];
@@ -449,6 +505,8 @@ __global__ void __launch_bounds__(256) dwconv_fwd_bulk_kernel(const T* __restric
         o.z = __bfloat162float(__float2bfloat16_rn(o.z)); o.w = __bfloat162float(__float2bfloat16_rn(o.w));
       }
       st4(z2 + (base + r + (int64_t)(j0 + jj) * dil) * H + c, o);
+      // (input row jj has left every window of this thread's channels: its shared-memory row now keeps output jj)
+      if (rs2_out != nullptr) st4(tile + (size_t)jj * H + c, o);
       if (do_stats) {
         const float4 q = prelu4(o, a2);
         s += (q.x + q.y) + (q.z + q.w);
@@ -461,6 +519,14 @@ __global__ void __launch_bounds__(256) dwconv_fwd_bulk_kernel(const T* __restric
     acc[1] += (double)s2;
   }
   if (!waited) ew_mbar_wait(&bar, 0);  // never leave with copies in flight
+  if (rs2_out != nullptr) {
+    __syncthreads();
+    for (int jj = wid; jj < nj; jj += nwarp) {
+      float mu, rstd;
+      row_stats_of(tile + (size_t)jj * H, a2, mu, rstd);
+      if (lane == 0) reinterpret_cast<float2*>(rs2_out)[base + r + (int64_t)(j0 + jj) * dil] = make_float2(mu, rstd);
+    }
+  }
   if (do_stats) {
     block_sum<2>(acc, red);
     if (threadIdx.x == 0) {
@@ -1146,9 +1212,25 @@ int run_prep_normfold(const float* W, const float* gamma, const float* beta, int
   return check_launch("prep_normfold_kernel");
 }
 
+// true when run_dwconv_fwd can form the cLN per-frame statistics itself (the bulk-staged kernel): the caller then skips
+// its two row_stats launches per block and passes the statistics buffers as rs1_out / rs2_out
+// Measured (B200, causal cLN, 32 x 4 s forward): fp32 storage 13.16 -> 12.14 ms with the statistics formed in the
+// depthwise kernel; bf16 storage 9.49 -> 9.63 ms (the two row_stats passes it replaces read half the bytes, the extra
+// work in the kernel is the same) — so the default fuses for fp32-stored activations only.  CTN_ROWSTAT_FUSION=0 / 1
+// forces it off / on for both (A/B).
+bool dwconv_fwd_fuses_rowstats(int H, int P, int bf16) {
+  static const int mode = getenv("CTN_ROWSTAT_FUSION") == nullptr ? -1 : (getenv("CTN_ROWSTAT_FUSION")[0] == '0' ? 0 : 1);
+  if (mode == 0 || (mode < 0 && bf16)) return false;
+  const size_t esz = bf16 ? 2 : 4;
+  return (dw_bulk_mask() & 1) && ((size_t)H * esz) % 16 == 0 && (size_t)(DWF_TJ + P - 1) * H * esz <= 160 * 1024 &&
+         P >= 1 && P <= MAXP;
+}
+
 int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const float* gamma1, const float* beta1,
                    const float* Wd, int M, int K, int H, int P, int dil, int causal, float* z2, double* stat_out,
-                   const float* alpha2, cudaStream_t s, int bf16) {
+                   const float* alpha2, cudaStream_t s, int bf16, float* rs1_out, float* rs2_out) {
+  CTN_REQUIRE((rs1_out == nullptr && rs2_out == nullptr) || (dwconv_fwd_fuses_rowstats(H, P, bf16) && alpha2 != nullptr),
+              "dwconv_fwd: in-kernel row statistics need the bulk-staged kernel (and alpha2)");
   CTN_REQUIRE(H % 4 == 0, "dwconv: H must be a multiple of 4 (got %d)", H);
   CTN_REQUIRE(P >= 1 && P <= MAXP, "dwconv: kernel size P must be in [1,%d] (got %d)", MAXP, P);
   CTN_REQUIRE(causal || (P % 2 == 1), "dwconv: non-causal needs odd P (reference output length changes otherwise)");
@@ -1164,7 +1246,7 @@ int run_dwconv_fwd(const float* z1, const float* alpha1, NormStats st1, const fl
       CTN_CUDA(cudaFuncSetAttribute(dwconv_fwd_bulk_kernel<PT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                     (int)bulk_smem));                                                                  \
     launch_kernel(dwconv_fwd_bulk_kernel<PT, TY>, grid, block_for_channels(H), bulk_smem, s, zi, alpha1, st1, gamma1,  \
-                  beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2);                                              \
+                  beta1, Wd, K, H, P, dil, cshift, zo, stat_out, alpha2, rs1_out, rs2_out);                            \
   } while (0)
     if (bf16) {
       const __nv_bfloat16* zi = reinterpret_cast<const __nv_bfloat16*>(z1);

@@ -84,10 +84,12 @@ int launch_wgrad_simt(const WgradArgs& a, cudaStream_t s);
 int run_encoder_fwd(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int run_encoder_bwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int run_row_stats(const float*, const float*, int64_t, int, float*, cudaStream_t, int bf16 = 0);
+bool dwconv_fwd_fuses_rowstats(int H, int P, int bf16);
 int run_prep_normfold(const float*, const float*, const float*, int, int, int, int64_t, float*, float*, float*, int64_t,
                       int64_t, cudaStream_t);
 int run_dwconv_fwd(const float*, const float*, NormStats, const float*, const float*, const float*, int, int, int, int,
-                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0);
+                   int, int, float*, double*, const float*, cudaStream_t, int bf16 = 0, float* rs1_out = nullptr,
+                   float* rs2_out = nullptr);
 int run_dwconv_bwd(const float*, const float*, const float*, NormStats, const float*, const float*, const float*, int,
                    int, int, int, int, int, float*, float*, float*, float*, double*, float*, int, cudaStream_t);
 int run_norm_bwd_reduce(const float*, const float*, const float*, NormStats, const float*, int, int, int, float*,
@@ -539,11 +541,18 @@ static int model_forward(const Ctx& X, const float* mixture, float* est) {
       a.half = half; a.d_bf16 = half;  // z1 stored as bf16
       CTN_TRY(launch_gemm(a, s));
     }
-    if (cln) CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s, half));
+    // cLN: the per-frame statistics of prelu(z1) and prelu(z2) come out of the depthwise kernel itself when it stages its
+    // rows in shared memory (elementwise.cu); otherwise one row_stats pass over [F, H] each
+    const bool fuse_rs = cln && dwconv_fwd_fuses_rowstats(c.H, c.P, half);
+    if (cln && !fuse_rs)
+      CTN_TRY(run_row_stats(X.z1(b), X.blk(b, L.a1), F, c.H, const_cast<float*>(X.stats(b, 0).row), s, half));
     if (bn) CTN_TRY(bn_forward(X, b, 0, X.z1(b)));
     CTN_TRY(run_dwconv_fwd(X.z1(b), X.blk(b, L.a1), X.stats(b, 0), X.gam(b, 0), X.bet(b, 0), X.blk(b, L.Wd), M, K,
-                           c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s, half));
-    if (cln) CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s, half));
+                           c.H, c.P, dil, c.causal, X.z2(b), X.stat_out(b, 1), X.blk(b, L.a2), s, half,
+                           fuse_rs ? const_cast<float*>(X.stats(b, 0).row) : nullptr,
+                           fuse_rs ? const_cast<float*>(X.stats(b, 1).row) : nullptr));
+    if (cln && !fuse_rs)
+      CTN_TRY(run_row_stats(X.z2(b), X.blk(b, L.a2), F, c.H, const_cast<float*>(X.stats(b, 1).row), s, half));
     if (bn) {  // statistics of prelu(z2) -> (s, t) -> this block's folded pointwise weight and its operand planes
       CTN_TRY(bn_forward(X, b, 1, X.z2(b)));
       float* W2g = X.at<float>(p.W2g) + (int64_t)b * c.B * c.H;
