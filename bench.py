@@ -498,13 +498,27 @@ def main():
         tot += e0.elapsed_time(e1) * 1e-3
     t_k = tot / reps
     flops = 2.0 * F * Bc * Hc
-    ach = flops / t_k / 1e12
+    # algorithmic bytes of one launch: both operands read once, the output written once (weight gradient: fp32 [H, B];
+    # forward conv: fp32 [F, H] out, [F, B] in)
+    alg_bytes = 4.0 * F * (Bc + Hc) + (4.0 * Hc * Bc if train else 0.0)
     traffic, traffic_src = profiled_traffic(ksub)
-    roofline = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": pk_src + ", bf16 burst (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the "
-                "ceiling of this fraction is 1/3)", "launch_us": t_k * 1e6, "alg_flops_per_launch": flops,
-                "alg_bytes_per_launch": 4.0 * F * (Bc + Hc), "launches_per_step": n_launch,
+    # which roofline binds this kernel: its arithmetic intensity (B H / (2 (B + H)) = 85 flop/B at the paper widths)
+    # against the machine's ridge (measured bf16 peak / measured copy bandwidth = ~250 flop/B) -> the HBM roof.  The
+    # tensor-pipe figure is kept next to it (the x3 operand split issues 3 MMAs per algorithmic MAC: its ceiling is 1/3).
+    t_hbm, t_tensor = alg_bytes / (pk["hbm_gbs"] * 1e9), flops / (pk["bf16_tflops"] * 1e12)
+    tensor_view = {"bound": "tensor", "achieved": flops / t_k / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                   "frac": flops / t_k / 1e12 / pk["bf16_tflops"],
+                   "note": "bf16 burst peak; the bf16x3 split issues 3 MMAs per algorithmic MAC, so 1/3 is this fraction's ceiling"}
+    hbm_view = {"bound": "hbm", "achieved": alg_bytes / t_k / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / t_k / 1e9 / pk["hbm_gbs"]}
+    main, other = (hbm_view, tensor_view) if t_hbm >= t_tensor else (tensor_view, hbm_view)
+    roofline = {"kernel": kname, **main, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk_src + (", copy bandwidth (burst)" if main["bound"] == "hbm" else ", bf16 burst"),
+                "binding": f"arithmetic intensity {flops / alg_bytes:.0f} flop/B vs ridge "
+                           f"{pk['bf16_tflops'] * 1e3 / pk['hbm_gbs']:.0f} flop/B: bound time hbm {t_hbm * 1e6:.2f} us, "
+                           f"tensor {t_tensor * 1e6:.2f} us",
+                "other_roof": other, "launch_us": t_k * 1e6, "alg_flops_per_launch": flops,
+                "alg_bytes_per_launch": alg_bytes, "launches_per_step": n_launch,
                 "share_of_step": n_launch * t_k / (secs / args.steps)}
 
     # whole-step algorithmic rates (SURVEY §8d per-frame figures x frames)
