@@ -397,6 +397,19 @@ ts_gemm_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const float mur = mu * r;
       float s1 = 0.f, s2 = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * dstride);
+      if (RES) {
+        // The residual tile [128 frames x n channels] is pulled into L2 while the MMAs of this segment run: the coalesced
+        // phase below reads it in dependent rounds of 4 row-loads per 32-column chunk (8 rounds per 256-column tile), and
+        // from HBM each round cost ~2k cycles — the whole epilogue of the contracting conv was residual-load latency
+        // (8 x 60 s forward: 436 us per launch against a 241 us HBM bound, with the MMAs waiting on the single
+        // accumulator buffer).
+        const int et = (warp - 12) * 32 + lane, lpr = (s.n + 31) >> 5;  // 128-byte lines per row
+        for (int l = et; l < TS_MT * lpr; l += 32 * TS_EPI_WARPS) {
+          const int rr = l / lpr, cc = l - rr * lpr;
+          const int64_t ff = (int64_t)s.ft * TS_MT + rr;
+          if (ff < a.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ff * O + s.c0 + cc * 32));
+        }
+      }
       mbar_wait(d_full + db, dph);
       tc_fence_after();
       if (row == 0 && sidx < 8) TST(216 + sidx);
