@@ -977,6 +977,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 #define CTN_NR_TK 16
 #endif
 constexpr int NR_TK = CTN_NR_TK;
+#ifndef CTN_NR_U
+#define CTN_NR_U 4
+#endif
+constexpr int NR_U = CTN_NR_U;  // frames (2 x NR_U independent 16-byte loads) in flight per thread
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ dn, const float* __restrict__ z,
                                                               const float* __restrict__ alpha, NormStats st,
                                                               const float* __restrict__ gamma, int K, int Ch,
@@ -1004,11 +1008,11 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
     const float4 g = ld4(gamma + c);
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s = 0.f, s2 = 0.f;
-    for (int kk = 0; kk < nk; kk += 4) {
-      float4 zv[4], dv[4];
-      float2 stv[4];
+    for (int kk = 0; kk < nk; kk += NR_U) {
+      float4 zv[NR_U], dv[NR_U];
+      float2 stv[NR_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NR_U; ++u) {
         const bool vk = kk + u < nk;
         const int64_t f = base + k0 + kk + u;
         zv[u] = vk ? ld4(z + f * Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1016,7 +1020,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
         stv[u] = (vk && st.row != nullptr) ? reinterpret_cast<const float2*>(st.row)[f] : s_st;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NR_U; ++u) {
         if (kk + u >= nk) break;
         const float mu = stv[u].x, r = stv[u].y;
         const float4 v = hasp ? prelu4(zv[u], a) : zv[u];
@@ -1053,7 +1057,12 @@ constexpr int GA_TK = CTN_GA_TK;
 #define CTN_GA_U 4
 #endif
 constexpr int GA_U = CTN_GA_U;
-__global__ void __launch_bounds__(256) gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
+#ifdef CTN_GA_MINB
+#define CTN_GA_BOUNDS __launch_bounds__(256, CTN_GA_MINB)
+#else
+#define CTN_GA_BOUNDS __launch_bounds__(256)
+#endif
+__global__ void CTN_GA_BOUNDS gln_bwd_apply_kernel(float* __restrict__ dn, const float* __restrict__ z,
                                                             const float* __restrict__ alpha, NormStats st,
                                                             const float* __restrict__ gamma, const double* __restrict__ redin,
                                                             int K, int Ch, float* __restrict__ dalpha) {
