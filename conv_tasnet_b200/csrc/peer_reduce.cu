@@ -16,7 +16,10 @@
 // and W-1 slices out per GPU, all links busy in both directions at once.
 //
 // Flag block (one per rank, zero-initialised, uint32): [0, 8) barrier-1 slots written by peers, [8, 16) barrier-2 slots,
-// [16] local epoch, [17] local finished-block counter, [18] sticky error (a wait gave up after PEER_TIMEOUT_NS).
+// [16] local epoch, [17] local finished-block counter, [18] sticky error: a wait gave up after the time-out (default 600 s
+// like NCCL's watchdog, CTN_PEER_TIMEOUT_S) — the kernel then traps, so the step fails loudly instead of applying
+// gradients that miss a rank.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -25,7 +28,6 @@ namespace ctn {
 namespace {
 
 constexpr int PEER_MAX = 8;
-constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;  // a rank that never arrives: give up
 
 struct PeerArgs {
   float* buf[PEER_MAX];
@@ -33,6 +35,7 @@ struct PeerArgs {
   int rank, world;
   int64_t offset4, count4;  // in float4 units
   float scale;
+  unsigned long long timeout_ns;  // a rank that never arrives: give up (and trap)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -57,12 +60,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // wait until the slot written by a peer reaches `want` (epochs only grow; the comparison is wrap-safe)
-__device__ __forceinline__ void wait_slot(uint32_t* slot, uint32_t want, uint32_t* err) {
+__device__ __forceinline__ void wait_slot(uint32_t* slot, uint32_t want, uint32_t* err, unsigned long long timeout_ns) {
   const unsigned long long t0 = global_ns();
   while ((int32_t)(ld_acquire_sys(slot) - want) < 0) {
-    if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+    if (global_ns() - t0 > timeout_ns) {
       *err = 1u;
-      break;
+      __threadfence_system();
+      __trap();
     }
   }
 }
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(512) peer_all_reduce_kernel(PeerArgs a) {
   const uint32_t e1 = 2u * s_epoch + 1u, e2 = e1 + 1u;
   // ---- 1. every rank's gradients are complete (their kernels precede this one on each rank's stream) ----
   if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(a.flags[threadIdx.x] + a.rank, e1);
-  if (threadIdx.x < W) wait_slot(mine + threadIdx.x, e1, mine + 18);
+  if (threadIdx.x < W) wait_slot(mine + threadIdx.x, e1, mine + 18, a.timeout_ns);
   __syncthreads();
   // ---- 2. my slice: sum over the ranks in rank order, scale, store into every rank's buffer ----
   const int64_t per = (a.count4 + W - 1) / W;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(512) peer_all_reduce_kernel(PeerArgs a) {
   if (s_last) {
     if (threadIdx.x < W) {
       st_release_sys(a.flags[threadIdx.x] + 8 + a.rank, e2);
-      wait_slot(mine + 8 + threadIdx.x, e2, mine + 18);
+      wait_slot(mine + 8 + threadIdx.x, e2, mine + 18, a.timeout_ns);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -150,6 +154,8 @@ int run_peer_all_reduce(float* const* bufs, uint32_t* const* flags, int rank, in
     a.flags[p] = flags[p];
   }
   a.rank = rank; a.world = world; a.offset4 = offset / 4; a.count4 = count / 4; a.scale = scale;
+  static const long long timeout_s = getenv("CTN_PEER_TIMEOUT_S") ? atoll(getenv("CTN_PEER_TIMEOUT_S")) : 600;
+  a.timeout_ns = (unsigned long long)(timeout_s > 0 ? timeout_s : 600) * 1000000000ull;
   // enough blocks to keep every link busy, few enough that all of them are resident while they wait at the barrier
   int dev = 0, sms = 148;
   CTN_CUDA(cudaGetDevice(&dev));
