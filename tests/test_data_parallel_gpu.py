@@ -25,6 +25,7 @@ def _free_port():
 
 def _worker(rank, world, port, q, backend="nccl", peer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("CTN_PEER_TIMEOUT_S", "60")  # a rank that never arrives fails the test instead of hanging it
     if backend == "nccl":
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -141,6 +142,7 @@ def _worker(rank, world, port, q, backend="nccl", peer=False):
 def _peer_worker(rank, world, port, backend, same_gpu):
     """the one-kernel peer-memory all-reduce (csrc/peer_reduce.cu) against the same sum formed by torch, bit for bit"""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("CTN_PEER_TIMEOUT_S", "60")
     dev = 0 if same_gpu else rank
     torch.cuda.set_device(dev)
     if backend == "nccl":
