@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x,
   pdl_wait();
   constexpr int VN = RowVec<T>::N;           // channels per 16-byte load
   constexpr int NVT = 512 / (32 * VN);       // loads per lane and row (fp32: 4, bf16: 2)
-  constexpr int RPW = VN == 8 ? 1 : 2;       // rows per warp (measured in the config-2 forward, F = 102k x 512: fp32 1 -> 43.5,
+#ifndef CTN_RS_RPW_BF16
+#define CTN_RS_RPW_BF16 1
+#endif
+  constexpr int RPW = VN == 8 ? CTN_RS_RPW_BF16 : 2;       // rows per warp (measured in the config-2 forward, F = 102k x 512: fp32 1 -> 43.5,
                                              // 2 -> 42.8 us; bf16 1 -> 44.7, 4 -> 59 us (89 registers, 2 blocks per SM))
   const int lane = threadIdx.x & 31;
   const int64_t f0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
@@ -1209,7 +1212,7 @@ static int block_for_channels(int Ch) {
 int run_row_stats(const float* x, const float* alpha, int64_t F, int Ch, float* rowstat, cudaStream_t s, int bf16) {
   CTN_REQUIRE(Ch % 4 == 0, "row_stats: channels must be a multiple of 4 (got %d)", Ch);
   if (bf16)
-    launch_kernel(row_stats_kernel<__nv_bfloat16>, cdiv(F, 8 * 1), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), alpha, F, Ch, rowstat);
+    launch_kernel(row_stats_kernel<__nv_bfloat16>, cdiv(F, 8 * CTN_RS_RPW_BF16), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), alpha, F, Ch, rowstat);
   else
     launch_kernel(row_stats_kernel<float>, cdiv(F, 8 * 2), 256, 0, s, x, alpha, F, Ch, rowstat);
   return check_launch("row_stats_kernel");
