@@ -192,3 +192,22 @@ def test_dispatcher_ops_are_registered_with_fake_kernels():
         assert torch.ops.ctn_b200.pit_backward(src, est, lens, coef, loss).shape == est.shape
     with pytest.raises(Exception):  # no CPU kernel: the op refuses CPU tensors instead of falling back
         torch.ops.ctn_b200.model_forward(torch.zeros(ops.param_floats(cfg)), torch.zeros(2, 400), cfg, False)
+
+
+def test_peer_all_reduce_rejects_bad_arguments_before_touching_the_gpu(lib):
+    """ctn_peer_all_reduce (the one-kernel gradient exchange) validates its arguments on the host: world size, rank,
+    4-float granularity, unmapped buffers — every error is reported through ctn_last_error, nothing is launched"""
+    L = lib.lib()
+    bufs = (ctypes.c_void_p * 8)(*[0x1000 * (i + 1) for i in range(8)])
+    flags = (ctypes.c_void_p * 8)(*[0x100000 + 0x100 * i for i in range(8)])
+    assert L.ctn_peer_all_reduce(bufs, flags, 0, 1, 0, 1024, 1.0, None) != 0 and b"world size" in L.ctn_last_error()
+    assert L.ctn_peer_all_reduce(bufs, flags, 0, 9, 0, 1024, 1.0, None) != 0 and b"world size" in L.ctn_last_error()
+    assert L.ctn_peer_all_reduce(bufs, flags, 2, 2, 0, 1024, 1.0, None) != 0 and b"rank" in L.ctn_last_error()
+    assert L.ctn_peer_all_reduce(bufs, flags, 0, 2, 2, 1024, 1.0, None) != 0 and b"multiples of 4" in L.ctn_last_error()
+    assert L.ctn_peer_all_reduce(bufs, flags, 0, 2, 0, 1022, 1.0, None) != 0 and b"multiples of 4" in L.ctn_last_error()
+    holes = (ctypes.c_void_p * 8)(0x1000, None)
+    assert L.ctn_peer_all_reduce(holes, flags, 0, 2, 0, 1024, 1.0, None) != 0 and b"not mapped" in L.ctn_last_error()
+    odd = (ctypes.c_void_p * 8)(0x1000, 0x2004)
+    assert L.ctn_peer_all_reduce(odd, flags, 0, 2, 0, 1024, 1.0, None) != 0 and b"16-byte aligned" in L.ctn_last_error()
+    assert L.ctn_peer_export(None, ctypes.create_string_buffer(64)) != 0
+    assert L.ctn_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) != 0
